@@ -1,0 +1,213 @@
+/*
+ * life_b200.h — C ABI of the B200-native LIFE hot path (D2Q9 lattice-Boltzmann step + immersed-boundary
+ * interpolate / spread), implemented in hand-written sm_100a CUDA (life_b200/csrc/).
+ *
+ * The reference (joconnor22/LIFE v1.0.3) has no plugin/FFI layer: it is one statically linked C++ binary in which
+ * GridClass exposes its arrays to ObjectsClass / IBMNodeClass through `friend` (inc/Grid.h:32-33).  The seam this
+ * header cuts is therefore the set of member-function *bodies* on the hot path; every entry point below names the
+ * reference function(s) whose body it replaces (file:line relative to the reference tree).  INTEGRATION.md shows
+ * the patch a LIFE maintainer applies to call them.
+ *
+ * Conventions
+ *   - plain C, no CUDA/torch types in any signature; every function returns 0 on success or a LIFE_E_* code and
+ *     latches a message readable with life_last_error().  The reference's own convention is ERROR(msg) → print +
+ *     exit(99) (inc/Utils.h:72-77); the host shim (life_b200/host) maps non-zero to exactly that.
+ *   - all host arrays are in the REFERENCE layout: node id = i*Ny + j (x-major, y fastest; src/Grid.cpp:70),
+ *     f[id*9 + v], u[id*2 + d], rho[id], D2Q9 numbering of src/Grid.cpp:1247-1250.  The library converts to its own
+ *     device layout (SoA planes, padded column pitch, ghost row/column ring).
+ *   - with nranks > 1 each rank (= one process, one GPU) owns the x-slab of columns [i_begin, i_end) returned by
+ *     life_slab(); "the lattice" in every array argument below then means that slab (a contiguous chunk of the
+ *     global reference array because x is the slow index).
+ *   - caller owns every pointer passed in; the library never keeps a host pointer after the call returns.
+ *   - one host thread per context, no re-entrancy.  Work is enqueued on the context's CUDA stream;
+ *     functions that return data to the host synchronise that stream, the others return after enqueue.
+ *   - there is NO CPU fallback: life_create fails with LIFE_E_CUDA if no sm_100 device is usable.
+ */
+#ifndef LIFE_B200_H
+#define LIFE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LIFE_ABI_VERSION 1
+
+/* lattice-site / wall types: values of eLatType, inc/defs.h:52 */
+enum {
+	LIFE_FLUID = 0,      /* eFluid      (a wall of this type is periodic) */
+	LIFE_WALL = 1,       /* eWall       */
+	LIFE_VELOCITY = 2,   /* eVelocity   */
+	LIFE_FREESLIP = 3,   /* eFreeSlip   */
+	LIFE_PRESSURE = 4,   /* ePressure   */
+	LIFE_CONVECTIVE = 5  /* eConvective (right wall only, src/Grid.cpp:919-922) */
+};
+
+/* collision operator: BGK (src/Grid.cpp:237-244) or central moments (#define CENTRAL_MOMENTS, src/Grid.cpp:106-233) */
+enum { LIFE_BGK = 0, LIFE_CENTRAL_MOMENTS = 1 };
+
+/* error codes */
+enum {
+	LIFE_OK = 0,
+	LIFE_E_ARG = 1,      /* bad argument / inconsistent configuration            */
+	LIFE_E_CUDA = 2,     /* CUDA runtime error, or no usable sm_100 device       */
+	LIFE_E_NCCL = 3,     /* NCCL error                                           */
+	LIFE_E_STATE = 4,    /* call out of order (e.g. step before upload)          */
+	LIFE_E_SUPPORT = 5,  /* a marker has more than 9 support sites (src/IBMNode.cpp:171-172) */
+	LIFE_E_NOMEM = 6
+};
+
+/* kernel selection for the bulk stream+collide sweep (all produce identical results; bench.py compares them) */
+enum {
+	LIFE_KERNEL_AUTO = 0,
+	LIFE_KERNEL_DIRECT = 1,  /* one node per thread, shifted global stores                          */
+	LIFE_KERNEL_STAGED = 2   /* column tiles staged through shared memory, 16-byte aligned row stores */
+};
+
+/*
+ * Everything the kernels read from inc/params.h and from the GridClass constructor (src/Grid.cpp:1232-1289),
+ * as run-time values.  Zero-initialise, then fill.
+ */
+typedef struct life_config {
+	int32_t abi_version;       /* LIFE_ABI_VERSION */
+	int32_t collision;         /* LIFE_BGK | LIFE_CENTRAL_MOMENTS                      (params.h:26)      */
+	int64_t Nx, Ny;            /* GLOBAL lattice size; 64-bit (the reference's int overflows at 15447^2) (params.h:46-47) */
+	double omega;              /* relaxation frequency                                  (params.h:83-94)   */
+	int32_t wall_left, wall_right, wall_bottom, wall_top; /* LIFE_* site types          (params.h:65-68)   */
+	double inlet_ramp;         /* INLET_RAMP in seconds, <= 0: no ramp                  (params.h:27)      */
+	double Dx, Dt, Dm, Drho;   /* lattice scalings                                      (Grid.cpp:1257-1260) */
+	double womersley;          /* WOMERSLEY number, <= 0: steady force_xy               (params.h:28)      */
+	double height_p, nu_p;     /* used by the Womersley period only                     (Grid.cpp:59-60)   */
+	double gravity_x, gravity_y, dpdx, dpdy;  /* used by the Womersley forcing only     (Grid.cpp:59-60)   */
+	int32_t ordered;           /* ORDERED: spread sums each site's contributions in marker order, bit-repeatable (params.h:30) */
+	int32_t device;            /* CUDA device ordinal; -1 = the calling thread's current device               */
+	void *stream;              /* cudaStream_t to enqueue on; NULL = the library creates its own               */
+	int32_t rank, nranks;      /* x-slab decomposition; nranks <= 1: single GPU                                */
+	const void *nccl_id;       /* 128-byte ncclUniqueId shared by all ranks (life_nccl_unique_id); NULL iff nranks <= 1 */
+	int32_t kernel;            /* LIFE_KERNEL_*                                                                 */
+	int32_t reserved[7];
+} life_config;
+
+typedef struct life_ctx life_ctx;
+
+/* ---- life cycle ------------------------------------------------------------------------------------------------- */
+
+int life_abi_version(void);
+
+/* Fill `out128` with a fresh ncclUniqueId (rank 0 calls this and broadcasts the bytes by any means). */
+int life_nccl_unique_id(void *out128);
+
+/* Allocation + lattice constants + site types / boundary list: replaces the GridClass constructor's allocation
+ * (src/Grid.cpp:1267-1279) and the type / BCVec construction of initialiseGrid (src/Grid.cpp:925-951). */
+int life_create(const life_config *cfg, life_ctx **out);
+int life_destroy(life_ctx *ctx);
+
+/* Message of the last failure on this context (ctx == NULL: last failure of life_create on this thread). */
+const char *life_last_error(const life_ctx *ctx);
+
+/* Columns [*i_begin, *i_end) of the global lattice owned by this context. */
+int life_slab(const life_ctx *ctx, int64_t *i_begin, int64_t *i_end);
+
+/* ---- state in / out --------------------------------------------------------------------------------------------- */
+
+/*
+ * Receives what initialiseGrid (src/Grid.cpp:954-1058) or readRestart (src/Grid.cpp:1072-1160) produced on the host.
+ *   f          [n*9]  post-stream populations (required)
+ *   rho, u     [n], [n*2]  start-of-step macroscopics (u_n / rho_n of the first step).  Both NULL: derived from f
+ *                     and the forces, which is what they equal after any completed step.
+ *   force_xy   [n*2]  Cartesian body force, NULL = 0      (src/Grid.cpp:1035-1045)
+ *   force_ibm  [n*2]  spread IBM force of the last step, NULL = 0 (restart only)
+ *   u_in       [Ny*2] inlet velocity profile, NULL = 0    (src/Grid.cpp:954-996)
+ *   rho_in     [Ny]   pressure-boundary density, NULL = 1 (src/Grid.cpp:1277-1278)
+ * n = (i_end - i_begin) * Ny.
+ */
+int life_upload_state(life_ctx *ctx, const double *f, const double *rho, const double *u, const double *force_xy,
+                      const double *force_ibm, const double *u_in, const double *rho_in);
+
+/* rho [n], u [n*2] as GridClass::rho / GridClass::u hold them at the end of a step (either may be NULL).
+ * Replaces the reads of writeInfo (src/Grid.cpp:559-588) and writeVTK (src/Grid.cpp:858-889). */
+int life_download_macro(life_ctx *ctx, double *rho, double *u);
+
+/* Full state for writeRestart (src/Grid.cpp:1192-1221): f [n*9] in the reference convention (post-stream,
+ * pre-collision, at its own node), rho, u, force_ibm [n*2].  Any pointer may be NULL. */
+int life_download_state(life_ctx *ctx, double *f, double *rho, double *u, double *force_ibm);
+
+/* The scan of writeInfo (src/Grid.cpp:562-588): maximum of sqrt(ux^2+uy^2), and whether any node is NaN
+ * (*has_nan, with the first such node in i-major order in *nan_i, *nan_j — global indices).  All-ranks collective
+ * when nranks > 1 (every rank gets the global answer). */
+int life_max_speed(life_ctx *ctx, double *vmax, int32_t *has_nan, int64_t *nan_i, int64_t *nan_j);
+
+/* ---- the lattice-Boltzmann step ----------------------------------------------------------------------------------- */
+
+/* One pass of GridClass::lbmKernel (src/Grid.cpp:36-100) at time step t (GridClass::t, 1-based after a fresh start):
+ * convective speed (:477-495), [Womersley forcing :52-62], stream + collide (:103-246), macroscopic (:282-299),
+ * boundary conditions (:302-474) with the inlet ramp at Dt*t (:548-556), and the slab halo exchange.  Asynchronous. */
+int life_step(life_ctx *ctx, int32_t t);
+
+/* n consecutive life_step calls for t_first, t_first+1, ... (only valid without bodies, since the reference runs
+ * objectKernel between steps). */
+int life_step_n(life_ctx *ctx, int32_t t_first, int32_t n);
+
+/* Block until everything enqueued so far has finished; surfaces asynchronous CUDA/NCCL errors. */
+int life_sync(life_ctx *ctx);
+
+/* ---- immersed boundary ----------------------------------------------------------------------------------------------- */
+
+/*
+ * Marker state the host owns (written by the FEM solver src/FEMBody.cpp:192-193, computeDs src/IBMNode.cpp:182-204
+ * and computeEpsilon src/Objects.cpp:235-321): pos, vel [n*2] in physical units, ds, epsilon [n].
+ * ALL markers of the simulation on every rank.  The device recomputes every marker's support exactly as
+ * IBMNodeClass::findSupport does (src/IBMNode.cpp:139-179, delta of inc/Utils.h:220-232).
+ * May be called every sub-iteration.  Returns LIFE_E_SUPPORT if a marker collects more than 9 sites.
+ */
+int life_ibm_set_markers(life_ctx *ctx, int64_t n, const double *pos, const double *vel, const double *ds,
+                         const double *epsilon);
+
+/* ObjectsClass::ibmKernelInterp (src/Objects.cpp:102-117): clears force_ibm, then per marker
+ * IBMNodeClass::interpolate (src/IBMNode.cpp:26-48) + forceCalc (:51-58).  force_out [n*2], lattice units.
+ * Synchronises (the host FEM consumes the forces, src/FEMElement.cpp:53). */
+int life_ibm_interp(life_ctx *ctx, double *force_out);
+
+/* ObjectsClass::ibmKernelSpread (src/Objects.cpp:120-149): clears force_ibm, IBMNodeClass::spread
+ * (src/IBMNode.cpp:61-94) with the forces of the last life_ibm_interp (or life_ibm_set_forces) and the
+ * supports / ds / epsilon of the last life_ibm_set_markers; updateMacroscopic (:97-136) is implicit (rho, u are
+ * always evaluated from f and the current forces).  Asynchronous. */
+int life_ibm_spread(life_ctx *ctx);
+
+/* Overwrite the marker forces kept on the device (restart: src/Objects.cpp:1226-1257 stores them). */
+int life_ibm_set_forces(life_ctx *ctx, const double *force);
+
+/* Interpolated density / momentum of the last life_ibm_interp (IBMNodeClass::interpRho / interpMom). */
+int life_ibm_get_interp(life_ctx *ctx, double *interp_rho, double *interp_mom);
+
+/* ---- test hooks (bit-exact integer-map checks) ------------------------------------------------------------------------ */
+
+/* Supports as IBMNodeClass::supp holds them: count [n]; idx, jdx, dirac [n*9] in the reference's i-outer/j-inner order. */
+int life_ibm_get_supports(life_ctx *ctx, int32_t *count, int32_t *idx, int32_t *jdx, double *dirac);
+
+/* Boundary list: *n entries (pass arrays sized 2*(Nx_local+Ny), or NULL to query *n).  id = i_local*Ny + j in BCVec
+ * order (src/Grid.cpp:925-951); type = eLatType; normal_x/normal_y/normal_dir as getNormalVector returns them
+ * (src/Grid.cpp:498-545). */
+int life_get_boundary(life_ctx *ctx, int64_t *n, int64_t *id, int32_t *type, int32_t *normal_x, int32_t *normal_y,
+                      int32_t *normal_dir);
+
+/* Site type of every node [n] (GridClass::type). */
+int life_get_types(life_ctx *ctx, int32_t *type);
+
+/* ---- measurement hooks ---------------------------------------------------------------------------------------------------- */
+
+/* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
+int64_t life_launch_count(const life_ctx *ctx);
+
+/* Device milliseconds of the bulk stream+collide kernel, averaged over the life_step calls since the last call of this
+ * function (CUDA events recorded around that kernel on its own stream); *launches receives the count. */
+int life_bulk_kernel_ms(life_ctx *ctx, double *avg_ms, int64_t *launches);
+
+/* Enable (1) / disable (0) the per-launch event timing read by life_bulk_kernel_ms. */
+int life_set_profiling(life_ctx *ctx, int32_t on);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIFE_B200_H */

@@ -1,0 +1,215 @@
+// TEST INFRASTRUCTURE — NOT PRODUCT CODE.
+//
+// C-ABI harness around the UNMODIFIED reference sources (/root/reference/src/*.cpp, compiled in place by
+// oracle/Makefile with -Dprivate=public and the case's params.h force-included).  One shared object per
+// compile-time case: oracle/_ref/libref_<case>.so.  It lets tests/ and bench.py's cpu_baseline leg
+//   * run the reference's own time loop body (main.cpp:70-74: t++ ; grid.solver()),
+//   * call the individual stages of the hot path (GridClass::lbmKernel Grid.cpp:36, and the pieces of
+//     ObjectsClass::objectKernel Objects.cpp:26-60) one at a time, and
+//   * read / write the reference's state arrays in their native layout (AoS, id = i*Ny + j).
+// Nothing here computes anything on its own: every number comes out of reference code.
+// Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference) may load this.
+
+#include "Grid.h"
+#include "Objects.h"
+#include "FEMBody.h"
+#include "Utils.h"
+#include <unistd.h>
+#include <cstring>
+
+#define REF_API extern "C" __attribute__((visibility("default")))
+
+static GridClass *g_grid = nullptr;
+static ObjectsClass *g_obj = nullptr;
+
+// Construct grid + objects exactly as main.cpp:42-45 does, inside a scratch working directory (the GridClass
+// constructor deletes ./Results, Utils.cpp:56-58; ObjectsClass reads ./input/geometry.config, Objects.cpp:327).
+REF_API int ref_create(const char *workdir) {
+	if (g_grid != nullptr) return 1;
+	if (workdir != nullptr && workdir[0] != 0 && chdir(workdir) != 0) return 2;
+	g_grid = new GridClass();
+	g_obj = new ObjectsClass(*g_grid);
+	return 0;
+}
+
+REF_API void ref_destroy() {
+	delete g_obj; g_obj = nullptr;
+	delete g_grid; g_grid = nullptr;
+}
+
+// ---- compile-time case description ------------------------------------------------------------------------------
+REF_API void ref_dims(int *out) {
+	out[0] = Nx; out[1] = Ny;
+	out[2] = g_obj ? static_cast<int>(g_obj->iNode.size()) : 0;
+	out[3] = g_obj ? static_cast<int>(g_obj->iBody.size()) : 0;
+	out[4] = g_grid ? static_cast<int>(g_grid->BCVec.size()) : 0;
+}
+
+REF_API void ref_walls(int *out) {
+	out[0] = WALL_LEFT; out[1] = WALL_RIGHT; out[2] = WALL_BOTTOM; out[3] = WALL_TOP;
+}
+
+// bit0 CENTRAL_MOMENTS, bit1 ORDERED, bit2 UNI_EPSILON, bit3 WOMERSLEY, bit4 INLET_RAMP, bit5 hasIBM, bit6 hasFlex
+REF_API int ref_flags() {
+	int fl = 0;
+#ifdef CENTRAL_MOMENTS
+	fl |= 1;
+#endif
+#ifdef ORDERED
+	fl |= 2;
+#endif
+#ifdef UNI_EPSILON
+	fl |= 4;
+#endif
+#ifdef WOMERSLEY
+	fl |= 8;
+#endif
+#ifdef INLET_RAMP
+	fl |= 16;
+#endif
+	if (g_obj && g_obj->hasIBM) fl |= 32;
+	if (g_obj && g_obj->hasFlex) fl |= 64;
+	return fl;
+}
+
+// omega, Dx, Dt, Dm, Drho, inlet_ramp (or -1), womersley (or -1), dpdx, dpdy, gravityX, gravityY, height_p, nu_p, rho_p, subTol, uxInlet_p, uyInlet_p, ux0_p, uy0_p
+REF_API void ref_scalars(double *out) {
+	out[0] = omega; out[1] = g_grid->Dx; out[2] = g_grid->Dt; out[3] = g_grid->Dm; out[4] = g_grid->Drho;
+#ifdef INLET_RAMP
+	out[5] = INLET_RAMP;
+#else
+	out[5] = -1.0;
+#endif
+#ifdef WOMERSLEY
+	out[6] = WOMERSLEY;
+#else
+	out[6] = -1.0;
+#endif
+	out[7] = dpdx; out[8] = dpdy; out[9] = gravityX; out[10] = gravityY;
+	out[11] = height_p; out[12] = nu_p; out[13] = rho_p; out[14] = subTol;
+	out[15] = uxInlet_p; out[16] = uyInlet_p; out[17] = ux0_p; out[18] = uy0_p;
+}
+
+// PROFILE (eProfileType) or -1 when the inlet is uniform
+REF_API int ref_profile() {
+#ifdef PROFILE
+	return PROFILE;
+#else
+	return -1;
+#endif
+}
+
+// ---- time loop pieces ----------------------------------------------------------------------------------------------
+REF_API int ref_get_t() { return g_grid->t; }
+REF_API void ref_set_t(int t) { g_grid->t = t; }
+
+// main.cpp:70-74 without the I/O: n passes of { t++ ; solver() }
+REF_API void ref_step(int n) {
+	for (int s = 0; s < n; s++) {
+		g_grid->t++;
+		g_grid->solver();
+	}
+}
+
+// Grid.cpp:36 alone (caller advances t with ref_set_t)
+REF_API void ref_lbm_kernel() { g_grid->lbmKernel(); }
+// Objects.cpp:26
+REF_API void ref_object_kernel() { g_obj->objectKernel(); }
+// The stages objectKernel() strings together (Objects.cpp:33-56), callable one at a time
+REF_API void ref_recompute_object_vals() { g_obj->recomputeObjectVals(); }
+REF_API void ref_ibm_interp() { g_obj->ibmKernelInterp(); }
+REF_API void ref_fem_kernel() { g_obj->femKernel(); }
+REF_API void ref_ibm_spread() { g_obj->ibmKernelSpread(); }
+REF_API int ref_get_subit() { return g_obj->subIt; }
+REF_API void ref_set_subit(int s) { g_obj->subIt = s; }
+REF_API double ref_get_subres() { return g_obj->subRes; }
+REF_API double ref_get_relax() { return g_obj->relax; }
+
+// ---- lattice state, native layout --------------------------------------------------------------------------------
+#define GETSET(name, member, T)                                                                                      \
+	REF_API void ref_get_##name(T *out) { memcpy(out, g_grid->member.data(), g_grid->member.size() * sizeof(T)); }   \
+	REF_API void ref_set_##name(const T *in) { memcpy(g_grid->member.data(), in, g_grid->member.size() * sizeof(T)); }
+GETSET(f, f, double)
+GETSET(f_n, f_n, double)
+GETSET(rho, rho, double)
+GETSET(rho_n, rho_n, double)
+GETSET(u, u, double)
+GETSET(u_n, u_n, double)
+GETSET(force_xy, force_xy, double)
+GETSET(force_ibm, force_ibm, double)
+GETSET(u_in, u_in, double)
+GETSET(rho_in, rho_in, double)
+
+REF_API void ref_get_type(int *out) {
+	for (size_t k = 0; k < g_grid->type.size(); k++) out[k] = static_cast<int>(g_grid->type[k]);
+}
+REF_API void ref_get_bcvec(int *out) { memcpy(out, g_grid->BCVec.data(), g_grid->BCVec.size() * sizeof(int)); }
+REF_API int ref_get_delu(double *out) {
+	memcpy(out, g_grid->delU.data(), g_grid->delU.size() * sizeof(double));
+	return static_cast<int>(g_grid->delU.size());
+}
+
+// NOTE: GridClass::streamCollide / getNormalVector / equilibrium are declared `inline` inside Grid.cpp, so they have no
+// external symbol and cannot be called from here.  The push map is recovered in tests/ from a full lbmKernel() pass
+// over tagged populations instead (rho_n = 0 makes the BGK equilibrium exactly zero: f_new[recv] = tag - omega*tag).
+
+// ---- markers ------------------------------------------------------------------------------------------------------------
+REF_API void ref_get_markers(double *pos, double *vel, double *force, double *ds, double *eps, int *body, int *flex) {
+	for (size_t n = 0; n < g_obj->iNode.size(); n++) {
+		IBMNodeClass &m = g_obj->iNode[n];
+		if (pos) { pos[2 * n] = m.pos[eX]; pos[2 * n + 1] = m.pos[eY]; }
+		if (vel) { vel[2 * n] = m.vel[eX]; vel[2 * n + 1] = m.vel[eY]; }
+		if (force) { force[2 * n] = m.force[eX]; force[2 * n + 1] = m.force[eY]; }
+		if (ds) ds[n] = m.ds;
+		if (eps) eps[n] = m.epsilon;
+		if (body) body[n] = m.iPtr->ID;
+		if (flex) flex[n] = static_cast<int>(m.iPtr->flex);
+	}
+}
+REF_API void ref_set_marker_force(const double *force) {
+	for (size_t n = 0; n < g_obj->iNode.size(); n++) {
+		g_obj->iNode[n].force[eX] = force[2 * n];
+		g_obj->iNode[n].force[eY] = force[2 * n + 1];
+	}
+}
+REF_API void ref_set_marker_posvel(const double *pos, const double *vel) {
+	for (size_t n = 0; n < g_obj->iNode.size(); n++) {
+		g_obj->iNode[n].pos[eX] = pos[2 * n]; g_obj->iNode[n].pos[eY] = pos[2 * n + 1];
+		g_obj->iNode[n].vel[eX] = vel[2 * n]; g_obj->iNode[n].vel[eY] = vel[2 * n + 1];
+	}
+}
+REF_API void ref_get_interp(double *rho, double *mom) {
+	for (size_t n = 0; n < g_obj->iNode.size(); n++) {
+		rho[n] = g_obj->iNode[n].interpRho;
+		mom[2 * n] = g_obj->iNode[n].interpMom[eX]; mom[2 * n + 1] = g_obj->iNode[n].interpMom[eY];
+	}
+}
+// supports: count[n]; idx/jdx/dirac [n*9 + s]
+REF_API void ref_get_supports(int *count, int *idx, int *jdx, double *dirac) {
+	for (size_t n = 0; n < g_obj->iNode.size(); n++) {
+		IBMNodeClass &m = g_obj->iNode[n];
+		count[n] = static_cast<int>(m.suppCount);
+		for (int s = 0; s < suppSize; s++) {
+			idx[n * suppSize + s] = m.supp[s].idx;
+			jdx[n * suppSize + s] = m.supp[s].jdx;
+			dirac[n * suppSize + s] = m.supp[s].diracVal;
+		}
+	}
+}
+// IBMNodeClass::findSupport (IBMNode.cpp:139) + computeDs (:182) on every marker, then ObjectsClass::computeEpsilon
+// (Objects.cpp:235) — what initialiseObjects (Objects.cpp:941) does, re-runnable after ref_set_marker_posvel.
+REF_API void ref_refresh_supports(int with_epsilon) {
+	for (size_t n = 0; n < g_obj->iNode.size(); n++) {
+		g_obj->iNode[n].findSupport();
+		g_obj->iNode[n].computeDs();
+	}
+	if (with_epsilon) {
+		int tKeep = g_grid->t;
+		g_grid->t = 0;                 // computeEpsilon only touches rigid bodies when t == 0 (Objects.cpp:261)
+		g_obj->computeEpsilon();
+		g_grid->t = tKeep;
+	}
+}
+
+// Restart files in the reference's own format (Grid.cpp:1163, Objects.cpp:1206) into ./Results/Restart
+REF_API void ref_write_restart() { Utils::writeRestart(*g_grid); }

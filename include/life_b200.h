@@ -61,8 +61,9 @@ enum {
 /* kernel selection for the bulk stream+collide sweep (all produce identical results; bench.py compares them) */
 enum {
 	LIFE_KERNEL_AUTO = 0,
-	LIFE_KERNEL_DIRECT = 1,  /* one node per thread, shifted global stores                          */
-	LIFE_KERNEL_STAGED = 2   /* column tiles staged through shared memory, 16-byte aligned row stores */
+	LIFE_KERNEL_DIRECT = 1,   /* one node per thread, shifted scalar stores                                          */
+	LIFE_KERNEL_SHUFFLE = 2,  /* two nodes per thread, 16-byte loads, y-moving populations re-aligned with warp shuffles */
+	LIFE_KERNEL_TMA = 3       /* persistent CTAs, column tiles moved by bulk async copies through shared memory      */
 };
 
 /*

@@ -1,0 +1,261 @@
+"""ctypes binding of the C ABI in include/life_b200.h (liblife_b200.so).
+
+This is the thinnest possible layer: one Python method per exported function, numpy arrays in the reference's
+layout in and out.  No arithmetic happens here and there is no fallback: if the shared library is missing or no
+B200 is present, construction raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "liblife_b200.so")
+
+ABI_VERSION = 1
+FLUID, WALL, VELOCITY, FREESLIP, PRESSURE, CONVECTIVE = range(6)
+BGK, CENTRAL_MOMENTS = 0, 1
+KERNEL_AUTO, KERNEL_DIRECT, KERNEL_SHUFFLE, KERNEL_TMA = 0, 1, 2, 3
+OK, E_ARG, E_CUDA, E_NCCL, E_STATE, E_SUPPORT, E_NOMEM = range(7)
+
+# every symbol include/life_b200.h declares (tests check the library exports exactly these)
+EXPORTS = [
+    "life_abi_version", "life_nccl_unique_id", "life_create", "life_destroy", "life_last_error", "life_slab",
+    "life_upload_state", "life_download_macro", "life_download_state", "life_max_speed", "life_step", "life_step_n",
+    "life_sync", "life_ibm_set_markers", "life_ibm_interp", "life_ibm_spread", "life_ibm_set_forces",
+    "life_ibm_get_interp", "life_ibm_get_supports", "life_get_boundary", "life_get_types", "life_launch_count",
+    "life_bulk_kernel_ms", "life_set_profiling",
+]
+
+
+class Config(C.Structure):
+    """struct life_config"""
+    _fields_ = [("abi_version", C.c_int32), ("collision", C.c_int32),
+                ("Nx", C.c_int64), ("Ny", C.c_int64),
+                ("omega", C.c_double),
+                ("wall_left", C.c_int32), ("wall_right", C.c_int32), ("wall_bottom", C.c_int32),
+                ("wall_top", C.c_int32),
+                ("inlet_ramp", C.c_double),
+                ("Dx", C.c_double), ("Dt", C.c_double), ("Dm", C.c_double), ("Drho", C.c_double),
+                ("womersley", C.c_double), ("height_p", C.c_double), ("nu_p", C.c_double),
+                ("gravity_x", C.c_double), ("gravity_y", C.c_double), ("dpdx", C.c_double), ("dpdy", C.c_double),
+                ("ordered", C.c_int32), ("device", C.c_int32),
+                ("stream", C.c_void_p),
+                ("rank", C.c_int32), ("nranks", C.c_int32),
+                ("nccl_id", C.c_void_p),
+                ("kernel", C.c_int32), ("reserved", C.c_int32 * 7)]
+
+    def __init__(self, **kw):
+        super().__init__()
+        self.abi_version = ABI_VERSION
+        self.device = -1
+        self.inlet_ramp = -1.0
+        self.womersley = -1.0
+        self.Drho = 1.0
+        self.wall_left = self.wall_right = self.wall_bottom = self.wall_top = WALL
+        for k, v in kw.items():
+            if not hasattr(self, k):
+                raise AttributeError(k)
+            setattr(self, k, v)
+
+
+class LifeError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("liblife_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """dlopen liblife_b200.so and declare the prototypes.  Raises if the library has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FileNotFoundError(LIB_PATH + " is missing: build it with `python -m life_b200.build` "
+                                           "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    L.life_abi_version.restype = C.c_int
+    L.life_nccl_unique_id.argtypes = [vp]
+    L.life_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    L.life_destroy.argtypes = [vp]
+    L.life_last_error.restype = C.c_char_p
+    L.life_last_error.argtypes = [vp]
+    L.life_slab.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
+    L.life_upload_state.argtypes = [vp] + [vp] * 7
+    L.life_download_macro.argtypes = [vp, vp, vp]
+    L.life_download_state.argtypes = [vp, vp, vp, vp, vp]
+    L.life_max_speed.argtypes = [vp, C.POINTER(dbl), C.POINTER(i32), C.POINTER(i64), C.POINTER(i64)]
+    L.life_step.argtypes = [vp, i32]
+    L.life_step_n.argtypes = [vp, i32, i32]
+    L.life_sync.argtypes = [vp]
+    L.life_ibm_set_markers.argtypes = [vp, i64, vp, vp, vp, vp]
+    L.life_ibm_interp.argtypes = [vp, vp]
+    L.life_ibm_spread.argtypes = [vp]
+    L.life_ibm_set_forces.argtypes = [vp, vp]
+    L.life_ibm_get_interp.argtypes = [vp, vp, vp]
+    L.life_ibm_get_supports.argtypes = [vp, vp, vp, vp, vp]
+    L.life_get_boundary.argtypes = [vp, C.POINTER(i64), vp, vp, vp, vp, vp]
+    L.life_get_types.argtypes = [vp, vp]
+    L.life_launch_count.restype = i64
+    L.life_launch_count.argtypes = [vp]
+    L.life_bulk_kernel_ms.argtypes = [vp, C.POINTER(dbl), C.POINTER(i64)]
+    L.life_set_profiling.argtypes = [vp, i32]
+    _lib = L
+    return L
+
+
+def nccl_unique_id():
+    buf = (C.c_char * 128)()
+    rc = load().life_nccl_unique_id(buf)
+    if rc:
+        raise LifeError(rc, load().life_last_error(None).decode())
+    return bytes(buf)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Context:
+    """One life_ctx.  Methods map one-to-one onto the C entry points."""
+
+    def __init__(self, cfg, nccl_id=None):
+        self.L = load()
+        self._id_buf = None
+        if nccl_id is not None:
+            self._id_buf = C.create_string_buffer(bytes(nccl_id), 128)
+            cfg.nccl_id = C.cast(self._id_buf, C.c_void_p)
+        self.cfg = cfg
+        h = C.c_void_p()
+        rc = self.L.life_create(C.byref(cfg), C.byref(h))
+        if rc:
+            raise LifeError(rc, self.L.life_last_error(None).decode())
+        self.h = h
+        b, e = C.c_int64(), C.c_int64()
+        self.L.life_slab(self.h, C.byref(b), C.byref(e))
+        self.i_begin, self.i_end = b.value, e.value
+        self.nxl = self.i_end - self.i_begin
+        self.Ny = int(cfg.Ny)
+        self.n_markers = 0
+
+    def _ck(self, rc):
+        if rc:
+            raise LifeError(rc, self.L.life_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.life_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- state ----
+    def upload_state(self, f, rho=None, u=None, force_xy=None, force_ibm=None, u_in=None, rho_in=None):
+        arrs = [_f64(a) for a in (f, rho, u, force_xy, force_ibm, u_in, rho_in)]
+        n = self.nxl * self.Ny
+        assert arrs[0].size == n * 9, "f has the wrong size for this slab"
+        self._ck(self.L.life_upload_state(self.h, *[_ptr(a) for a in arrs]))
+
+    def download_macro(self, rho=True, u=True):
+        r = np.empty((self.nxl, self.Ny)) if rho else None
+        v = np.empty((self.nxl, self.Ny, 2)) if u else None
+        self._ck(self.L.life_download_macro(self.h, _ptr(r), _ptr(v)))
+        return r, v
+
+    def download_state(self):
+        f = np.empty((self.nxl, self.Ny, 9))
+        r = np.empty((self.nxl, self.Ny))
+        v = np.empty((self.nxl, self.Ny, 2))
+        fi = np.empty((self.nxl, self.Ny, 2))
+        self._ck(self.L.life_download_state(self.h, _ptr(f), _ptr(r), _ptr(v), _ptr(fi)))
+        return dict(f=f, rho=r, u=v, force_ibm=fi)
+
+    def download_into(self, f=None, rho=None, u=None, force_ibm=None):
+        self._ck(self.L.life_download_state(self.h, _ptr(f), _ptr(rho), _ptr(u), _ptr(force_ibm)))
+
+    def download_macro_into(self, rho=None, u=None):
+        self._ck(self.L.life_download_macro(self.h, _ptr(rho), _ptr(u)))
+
+    def max_speed(self):
+        v, hn, ni, nj = C.c_double(), C.c_int32(), C.c_int64(), C.c_int64()
+        self._ck(self.L.life_max_speed(self.h, C.byref(v), C.byref(hn), C.byref(ni), C.byref(nj)))
+        return v.value, bool(hn.value), ni.value, nj.value
+
+    # ---- stepping ----
+    def step(self, t):
+        self._ck(self.L.life_step(self.h, int(t)))
+
+    def step_n(self, t_first, n):
+        self._ck(self.L.life_step_n(self.h, int(t_first), int(n)))
+
+    def sync(self):
+        self._ck(self.L.life_sync(self.h))
+
+    # ---- markers ----
+    def ibm_set_markers(self, pos, vel, ds, eps):
+        pos, vel, ds, eps = _f64(pos), _f64(vel), _f64(ds), _f64(eps)
+        n = len(ds)
+        self.n_markers = n
+        self._ck(self.L.life_ibm_set_markers(self.h, n, _ptr(pos), _ptr(vel), _ptr(ds), _ptr(eps)))
+
+    def ibm_interp(self):
+        out = np.empty((self.n_markers, 2))
+        self._ck(self.L.life_ibm_interp(self.h, _ptr(out)))
+        return out
+
+    def ibm_spread(self):
+        self._ck(self.L.life_ibm_spread(self.h))
+
+    def ibm_set_forces(self, force):
+        force = _f64(force)
+        self._ck(self.L.life_ibm_set_forces(self.h, _ptr(force)))
+
+    def ibm_get_interp(self):
+        r, m = np.empty(self.n_markers), np.empty((self.n_markers, 2))
+        self._ck(self.L.life_ibm_get_interp(self.h, _ptr(r), _ptr(m)))
+        return r, m
+
+    def ibm_get_supports(self):
+        n = self.n_markers
+        count = np.zeros(n, np.int32)
+        idx, jdx = np.zeros((n, 9), np.int32), np.zeros((n, 9), np.int32)
+        dirac = np.zeros((n, 9))
+        self._ck(self.L.life_ibm_get_supports(self.h, _ptr(count), _ptr(idx), _ptr(jdx), _ptr(dirac)))
+        return count, idx, jdx, dirac
+
+    # ---- test / measurement hooks ----
+    def boundary(self):
+        n = C.c_int64()
+        self._ck(self.L.life_get_boundary(self.h, C.byref(n), None, None, None, None, None))
+        ids = np.zeros(n.value, np.int64)
+        ty, nx, ny, nd = (np.zeros(n.value, np.int32) for _ in range(4))
+        self._ck(self.L.life_get_boundary(self.h, C.byref(n), _ptr(ids), _ptr(ty), _ptr(nx), _ptr(ny), _ptr(nd)))
+        return ids, ty, nx, ny, nd
+
+    def types(self):
+        t = np.zeros((self.nxl, self.Ny), np.int32)
+        self._ck(self.L.life_get_types(self.h, _ptr(t)))
+        return t
+
+    def launch_count(self):
+        return int(self.L.life_launch_count(self.h))
+
+    def set_profiling(self, on):
+        self._ck(self.L.life_set_profiling(self.h, int(bool(on))))
+
+    def bulk_kernel_ms(self):
+        ms, n = C.c_double(), C.c_int64()
+        self._ck(self.L.life_bulk_kernel_ms(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value

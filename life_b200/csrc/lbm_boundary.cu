@@ -1,0 +1,348 @@
+// Everything of the LBM step that touches only O(Nx + Ny) nodes:
+//   * site types, BCVec and normals                       (src/Grid.cpp:925-951, :498-545) — built on the host once
+//   * the y wrap-around of the ghost ring                 (periodic modulo of src/Grid.cpp:229, applied to the ring)
+//   * convective outlet speed                             (src/Grid.cpp:477-495)
+//   * boundary conditions + their macroscopic update      (src/Grid.cpp:87-98 → applyBCs :302-384, regularisedBC :387-465,
+//                                                          convectiveBC :468-474, Utils::extrapolate / zeroGradient
+//                                                          inc/Utils.h:137-217)
+// The boundary kernel runs after the bulk sweep (and the halo exchange) on the freshly streamed buffer; it needs the
+// *new* rho/u of up to two interior neighbours, which it recomputes from their nine populations.
+#include "ctx.h"
+#include "d2q9.cuh"
+#include <cmath>
+
+namespace life {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// host: type matrix of the slab, BCVec order, normals
+// ---------------------------------------------------------------------------------------------------------------------
+static inline int site_type(const life_config &c, int64_t i, int64_t j) {
+	int t = LIFE_FLUID;
+	if (i == 0) t = c.wall_left;
+	else if (i == c.Nx - 1) t = c.wall_right;
+	if (j == 0) t = c.wall_bottom;          // bottom/top override left/right at the corners (src/Grid.cpp:940-945)
+	else if (j == c.Ny - 1) t = c.wall_top;
+	return t;
+}
+
+int build_boundary(life_ctx *ctx) {
+	const life_config &c = ctx->cfg;
+	const int64_t Ny = c.Ny, nxl = ctx->L.nxl;
+	if (c.wall_left == LIFE_CONVECTIVE || c.wall_bottom == LIFE_CONVECTIVE || c.wall_top == LIFE_CONVECTIVE)
+		return fail(ctx, LIFE_E_ARG, "Currently convective BC only supported for right boundary");   // src/Grid.cpp:919-920
+	ctx->h_type.assign((size_t)(nxl * Ny), LIFE_FLUID);
+	ctx->h_bc.clear();
+	for (int64_t il = 0; il < nxl; il++) {
+		const int64_t i = ctx->i_begin + il;
+		const bool xedge = (i == 0 || i == c.Nx - 1);
+		for (int64_t j = 0; j < Ny; j++) {
+			if (!xedge && j != 0 && j != Ny - 1) continue;
+			const int t = site_type(c, i, j);
+			ctx->h_type[(size_t)(il * Ny + j)] = t;
+			if (t == LIFE_FLUID) continue;
+			BcNode b{};
+			b.il = (int32_t)il; b.j = (int32_t)j; b.type = (int8_t)t;
+			// getNormalVector, src/Grid.cpp:498-545
+			int nx = 0, ny = 0, nd = 0;
+			if (i == 0) { nx = 1; nd = 0; } else if (i == c.Nx - 1) { nx = -1; nd = 0; }
+			if (j == 0) { ny = 1; nd = 1; } else if (j == Ny - 1) { ny = -1; nd = 1; }
+			if (nx != 0 && ny != 0) {
+				const int tx = site_type(c, i + nx, j), ty = site_type(c, i, j + ny);
+				if (tx == LIFE_FLUID && ty == LIFE_FLUID)
+					return fail(ctx, LIFE_E_ARG, "Corner node is surrounded by fluid lattice sites");   // src/Grid.cpp:527-528
+				else if (tx == LIFE_FLUID) { nd = 0; ny = 0; }
+				else if (ty == LIFE_FLUID) { nd = 1; nx = 0; }
+			}
+			b.nx = (int8_t)nx; b.ny = (int8_t)ny; b.nd = (int8_t)nd;
+			ctx->h_bc.push_back(b);
+		}
+	}
+	ctx->n_bc = (int64_t)ctx->h_bc.size();
+	if (ctx->n_bc > 0) {
+		LIFE_CUDA(ctx, cudaMalloc(&ctx->bc, sizeof(BcNode) * ctx->n_bc));
+		LIFE_CUDA(ctx, cudaMemcpy(ctx->bc, ctx->h_bc.data(), sizeof(BcNode) * ctx->n_bc, cudaMemcpyHostToDevice));
+	}
+	return LIFE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// y wrap-around: a population pushed out through the top lands in ghost row Ny; the reference's modulo puts it in row 0
+// (and vice versa).  Only consumed where the receiving row is periodic (type eFluid), so only applied then.
+// Covers the ghost columns too, so corner populations end up where the x exchange expects them.
+// ---------------------------------------------------------------------------------------------------------------------
+// `after_exchange` = second pass of a multi-rank step (after the interior sweep, concurrent with the halo receive): it must
+// leave alone what the x exchange delivers — the cx = +1 planes of the first column, the cx = -1 planes of the last column —
+// and the ghost columns, which were wrapped by the first pass before they were sent.
+__global__ void k_wrap_y(double *f, Layout L, int wrap_to_bottom, int wrap_to_top, int after_exchange) {
+	const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (c > L.nxl + 1) return;
+	if (after_exchange && (c == 0 || c == L.nxl + 1)) return;
+	const bool skip_plus = after_exchange && c == 1;        // cx = +1 planes: 5 (cy=+1), 7 (cy=-1)
+	const bool skip_minus = after_exchange && c == L.nxl;   // cx = -1 planes: 8 (cy=+1), 6 (cy=-1)
+	const int64_t base = c * L.P;
+	if (wrap_to_bottom) {   // cy = +1 populations: v = 3, 5, 8
+		f[3 * L.S + base + JOFF] = f[3 * L.S + base + JOFF + L.Ny];
+		if (!skip_plus) f[5 * L.S + base + JOFF] = f[5 * L.S + base + JOFF + L.Ny];
+		if (!skip_minus) f[8 * L.S + base + JOFF] = f[8 * L.S + base + JOFF + L.Ny];
+	}
+	if (wrap_to_top) {      // cy = -1 populations: v = 4, 6, 7
+		f[4 * L.S + base + JOFF + L.Ny - 1] = f[4 * L.S + base + JOFF - 1];
+		if (!skip_minus) f[6 * L.S + base + JOFF + L.Ny - 1] = f[6 * L.S + base + JOFF - 1];
+		if (!skip_plus) f[7 * L.S + base + JOFF + L.Ny - 1] = f[7 * L.S + base + JOFF - 1];
+	}
+}
+
+int launch_wrap_y(life_ctx *ctx, cudaStream_t st, bool after_exchange) {
+	const int wb = ctx->cfg.wall_bottom == LIFE_FLUID, wt = ctx->cfg.wall_top == LIFE_FLUID;
+	if (!wb && !wt) return LIFE_OK;
+	const int64_t n = ctx->L.nxl + 2;
+	k_wrap_y<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ctx->fB, ctx->L, wb, wt, after_exchange ? 1 : 0);
+	ctx->launches++;
+	LIFE_CUDA(ctx, cudaGetLastError());
+	return LIFE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// shared device helpers: macroscopics of an arbitrary node recomputed from its populations
+// ---------------------------------------------------------------------------------------------------------------------
+struct ForceView {
+	int mode;                 // FXY_*
+	double ux, uy;            // uniform force_xy
+	const double *field;      // force_xy planes (FXY_FIELD)
+	const double *fibm;       // force_ibm planes or nullptr
+	int64_t S;
+	__device__ __forceinline__ void xy(int64_t idx, double &fx, double &fy) const {
+		if (mode == FXY_FIELD) { fx = field[idx]; fy = field[S + idx]; }
+		else { fx = ux; fy = uy; }
+	}
+	__device__ __forceinline__ void ibm(int64_t idx, double &fx, double &fy) const {
+		if (fibm) { fx = fibm[idx]; fy = fibm[S + idx]; } else { fx = 0.0; fy = 0.0; }
+	}
+};
+
+__device__ __forceinline__ void load9(const double *f, int64_t S, int64_t idx, double (&o)[NV]) {
+#pragma unroll
+	for (int v = 0; v < NV; v++) o[v] = f[v * S + idx];
+}
+
+// rho and u of GridClass::macroscopic (src/Grid.cpp:282-299): u = (sum c f + F_xy/2)/rho — no IBM force (mid-step value)
+__device__ __forceinline__ void macro_mid(const double *f, const Layout &L, const ForceView &fv, int64_t idx, double &rho,
+                                          double &ux, double &uy) {
+	double p[NV], mx, my, fx, fy;
+	load9(f, L.S, idx, p);
+	moments(p, rho, mx, my);
+	fv.xy(idx, fx, fy);
+	ux = (mx + 0.5 * fx) / rho;
+	uy = (my + 0.5 * fy) / rho;
+}
+
+// end-of-step value: u = (sum c f + (F_xy + F_ibm)/2)/rho (src/IBMNode.cpp:121-122; equals macroscopic() off-support)
+__device__ __forceinline__ void macro_end(const double *f, const Layout &L, const ForceView &fv, int64_t idx, double &rho,
+                                          double &ux, double &uy) {
+	double p[NV], mx, my, fx, fy, gx, gy;
+	load9(f, L.S, idx, p);
+	moments(p, rho, mx, my);
+	fv.xy(idx, fx, fy);
+	fv.ibm(idx, gx, gy);
+	ux = (mx + 0.5 * (fx + gx)) / rho;
+	uy = (my + 0.5 * (fy + gy)) / rho;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// convective outlet speed (src/Grid.cpp:477-495), on the rank that owns the last three columns.
+// One block; u of the previous step's end at columns Nx-1, Nx-2, Nx-3 is recomputed from the state buffer (or read from the
+// uploaded macroscopics on the first step).  The column mean is a fixed-shape tree sum (deterministic).
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_convective_speed(const double *f, const double *stored, Layout L, ForceView fv,
+                                                           double *delU) {
+	__shared__ double red[1024];
+	const int64_t c1 = L.nxl, c2 = L.nxl - 1, c3 = L.nxl - 2;   // local columns of i = Nx-1, Nx-2, Nx-3
+	double part = 0.0;
+	for (int64_t j = threadIdx.x; j < L.Ny; j += blockDim.x) {
+		const int64_t idx = L.at(c1, j + JOFF);
+		double rho, ux, uy;
+		if (stored) ux = stored[L.S + idx];
+		else macro_end(f, L, fv, idx, rho, ux, uy);
+		part += ux;
+	}
+	red[threadIdx.x] = part;
+	__syncthreads();
+	for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+		if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+		__syncthreads();
+	}
+	const double uOut = red[0] / (double)L.Ny;
+	for (int64_t j = threadIdx.x; j < L.Ny; j += blockDim.x) {
+		double r, a[2], b[2], c[2];
+		const int64_t i1 = L.at(c1, j + JOFF), i2 = L.at(c2, j + JOFF), i3 = L.at(c3, j + JOFF);
+		if (stored) {
+			a[0] = stored[L.S + i1]; a[1] = stored[2 * L.S + i1];
+			b[0] = stored[L.S + i2]; b[1] = stored[2 * L.S + i2];
+			c[0] = stored[L.S + i3]; c[1] = stored[2 * L.S + i3];
+		} else {
+			macro_end(f, L, fv, i1, r, a[0], a[1]);
+			macro_end(f, L, fv, i2, r, b[0], b[1]);
+			macro_end(f, L, fv, i3, r, c[0], c[1]);
+		}
+		delU[2 * j] = (-uOut / 2.0) * (3.0 * a[0] - 4.0 * b[0] + c[0]);
+		delU[2 * j + 1] = (-uOut / 2.0) * (3.0 * a[1] - 4.0 * b[1] + c[1]);
+	}
+}
+
+static ForceView force_view(life_ctx *ctx, const double uni[2]) {
+	ForceView fv{};
+	fv.mode = ctx->fxy_mode;
+	fv.ux = uni[0]; fv.uy = uni[1];
+	fv.field = ctx->fxyf;
+	fv.fibm = ctx->fibm_any ? ctx->fibm : nullptr;
+	fv.S = ctx->L.S;
+	return fv;
+}
+
+int launch_convective_speed(life_ctx *ctx, const StepScalars &sc) {
+	if (ctx->cfg.wall_right != LIFE_CONVECTIVE || ctx->i_end != ctx->cfg.Nx) return LIFE_OK;
+	if (ctx->L.nxl < 3) return fail(ctx, LIFE_E_ARG, "convective outlet needs the last three columns on one rank");
+	ForceView fv = force_view(ctx, sc.fxy_prev);
+	k_convective_speed<<<1, 1024, 0, ctx->stream>>>(ctx->fA, ctx->stored_macro_valid ? ctx->macro : nullptr, ctx->L, fv,
+	                                                ctx->delU);
+	ctx->launches++;
+	LIFE_CUDA(ctx, cudaGetLastError());
+	return LIFE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// boundary conditions, one thread per BCVec entry
+// ---------------------------------------------------------------------------------------------------------------------
+struct BcArgs {
+	const BcNode *bc;
+	int64_t n;
+	const double *fprev;      // state before this step (f_n): convective outlet, stale u_n component
+	double *f;                // freshly streamed populations (f)
+	const double *stored;     // uploaded u_n/rho_n if this is the first step, else nullptr
+	Layout L;
+	ForceView fcur;           // forces of this step (new macroscopics of neighbours)
+	ForceView fprv;           // forces in effect at the end of the previous step
+	const double *u_in, *rho_in, *delU;
+	double ramp;
+};
+
+template <int COLL>
+__global__ void __launch_bounds__(128) k_boundary(const BcArgs a) {
+	const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= a.n) return;
+	const BcNode bn = a.bc[b];
+	const Layout &L = a.L;
+	const int64_t idx = L.node(bn.il, bn.j);
+	const int nx = bn.nx, ny = bn.ny, nd = bn.nd, type = bn.type;
+
+	if (type == LIFE_CONVECTIVE) {   // convectiveBC, src/Grid.cpp:468-474: only the three incoming populations
+		const double dux = a.delU[2 * bn.j], duy = a.delU[2 * bn.j + 1];
+		a.f[2 * L.S + idx] = a.fprev[2 * L.S + idx] + 3.0 * W1 * (dux * -1.0 + duy * 0.0);
+		a.f[6 * L.S + idx] = a.fprev[6 * L.S + idx] + 3.0 * W2 * (dux * -1.0 + duy * -1.0);
+		a.f[8 * L.S + idx] = a.fprev[8 * L.S + idx] + 3.0 * W2 * (dux * -1.0 + duy * 1.0);
+		return;
+	}
+
+	double f[NV];
+	load9(a.f, L.S, idx, f);
+
+	// u_n / rho_n start as the end-of-previous-step values of this node (they are only read back in one case: the normal
+	// velocity of a pressure corner, which applyBCs leaves untouched)
+	double un[2] = {0.0, 0.0}, rhon = 1.0;
+	const bool corner = (nx != 0 && ny != 0);
+	if (type == LIFE_PRESSURE && corner) {
+		if (a.stored) { un[0] = a.stored[L.S + idx]; un[1] = a.stored[2 * L.S + idx]; }
+		else { double r; macro_end(a.fprev, L, a.fprv, idx, r, un[0], un[1]); }
+	}
+
+	// interior neighbours along the normal (inc/Utils.h:151-161, :200-210)
+	const int64_t i1 = idx + nx * L.P + ny, i2 = idx + 2 * (nx * L.P + ny);
+
+	// applyBCs, src/Grid.cpp:312-375
+	if (type == LIFE_WALL) {
+		un[0] = 0.0; un[1] = 0.0;
+	} else if (type == LIFE_VELOCITY) {
+		un[0] = a.u_in[2 * bn.j] * a.ramp;
+		un[1] = a.u_in[2 * bn.j + 1] * a.ramp;
+	} else {   // free slip / pressure: tangential velocity by 2nd-order zero gradient of the NEW u
+		double r1, u1[2], r2, u2[2];
+		macro_mid(a.f, L, a.fcur, i1, r1, u1[0], u1[1]);
+		macro_mid(a.f, L, a.fcur, i2, r2, u2[0], u2[1]);
+		const int dt = 1 - nd;
+		if (type == LIFE_FREESLIP) un[nd] = 0.0;
+		else rhon = a.rho_in[bn.j];
+		un[dt] = (4.0 / 3.0) * u1[dt] - (1.0 / 3.0) * u2[dt];
+	}
+
+	// regularisedBC, src/Grid.cpp:387-465
+	const int nn = nd == 0 ? nx : ny;
+	if (corner) {
+		if (type != LIFE_PRESSURE) {   // density extrapolated along the diagonal from the NEW rho (src/Grid.cpp:394)
+			double r1, r2, t0, t1;
+			macro_mid(a.f, L, a.fcur, i1, r1, t0, t1);
+			macro_mid(a.f, L, a.fcur, i2, r2, t0, t1);
+			rhon = 2.0 * r1 - r2;
+		}
+	} else {
+		double fplus = 0.0, fzero = 0.0;
+#pragma unroll
+		for (int v = 0; v < NV; v++) {
+			const int cn = nd == 0 ? kCx[v] : kCy[v];
+			if (cn == -nn) fplus += f[v];
+			else if (cn == 0) fzero += f[v];
+		}
+		if (type != LIFE_PRESSURE) rhon = (2.0 * fplus + fzero) / (1.0 - nn * un[nd]);
+		else un[nd] = nn * (1.0 - (2.0 * fplus + fzero) / rhon);
+	}
+
+	double feq[NV];
+#pragma unroll
+	for (int v = 0; v < NV; v++) feq[v] = equilibrium<COLL>(rhon, un[0], un[1], v);
+
+	double Sxx = 0.0, Syy = 0.0, Sxy = 0.0;
+#pragma unroll
+	for (int v = 0; v < NV; v++) {
+		const int cx = kCx[v], cy = kCy[v];
+		double fv = f[v];
+		if (corner) {
+			if (cx == nx || cy == ny) {
+				if (nx * cx + ny * cy == 0) fv = feq[v];                        // buried link
+				else fv = feq[v] + (f[LIFE_OPP(v)] - feq[LIFE_OPP(v)]);
+			}
+		} else {
+			const int cn = nd == 0 ? cx : cy;
+			if (cn == nn) fv = feq[v] + (f[LIFE_OPP(v)] - feq[LIFE_OPP(v)]);
+		}
+		const double fneq = fv - feq[v];
+		Sxx += cx * cx * fneq;
+		Syy += cy * cy * fneq;
+		Sxy += cx * cy * fneq;
+	}
+#pragma unroll
+	for (int v = 0; v < NV; v++) {
+		const int cx = kCx[v], cy = kCy[v];
+		const double w = v == 0 ? W0 : (v < 5 ? W1 : W2);
+		a.f[v * L.S + idx] = feq[v] + (w / (2.0 * CS4)) * (((cx * cx - CS2) * Sxx) + ((cy * cy - CS2) * Syy) + (2.0 * cx * cy * Sxy));
+	}
+}
+
+int launch_boundary(life_ctx *ctx, const StepScalars &sc) {
+	if (ctx->n_bc == 0) return LIFE_OK;
+	BcArgs a{};
+	a.bc = ctx->bc; a.n = ctx->n_bc;
+	a.fprev = ctx->fA; a.f = ctx->fB;
+	a.stored = ctx->stored_macro_valid ? ctx->macro : nullptr;
+	a.L = ctx->L;
+	a.fcur = force_view(ctx, sc.fxy_cur);
+	a.fprv = force_view(ctx, sc.fxy_prev);
+	a.u_in = ctx->u_in; a.rho_in = ctx->rho_in; a.delU = ctx->delU;
+	a.ramp = sc.ramp;
+	const unsigned blocks = (unsigned)((a.n + 127) / 128);
+	if (ctx->cfg.collision == LIFE_CENTRAL_MOMENTS) k_boundary<COLL_CM><<<blocks, 128, 0, ctx->stream>>>(a);
+	else k_boundary<COLL_BGK><<<blocks, 128, 0, ctx->stream>>>(a);
+	ctx->launches++;
+	LIFE_CUDA(ctx, cudaGetLastError());
+	return LIFE_OK;
+}
+
+}  // namespace life

@@ -1,0 +1,207 @@
+// Bulk sweep of the D2Q9 step: stream + collide of every node of a column range, fused in one pass over HBM.
+//
+// Replaces, for all nodes at once, the reference's hot loops 1 and 2 (src/Grid.cpp:65-84): streamCollide (:103-246) with
+// equilibrium (:249-264) and latticeForce (:267-279), and the macroscopic pass (:282-299) — the latter is not stored at
+// all: the start-of-step rho_n/u_n a node needs are recomputed from its own nine populations and the forces
+// (after every completed step u == (sum c f + (F_xy + F_ibm)/2) / sum f at every node).
+//
+// State convention = the reference's: the buffer holds post-stream, pre-collision populations at their own node.
+// Each thread reads the nine populations of its node(s) from `fin` (coalesced, 16-byte vector loads), collides, and
+// pushes population v to (c + cx, r + cy) of `fout`.  The ghost ring of the layout (ctx.h) absorbs pushes that leave
+// the slab or wrap around, so there is no modulo and no branch in here (the reference wraps with two `%` per
+// population, src/Grid.cpp:229).
+//
+// Algorithmic traffic: 9 loads + 9 stores of 8 B = 144 B per lattice update (+16 B when an IBM force field is read).
+//
+// Variants (cfg.kernel, identical results):
+//   DIRECT : one node per thread, scalar shifted stores.
+//   SHUFFLE: two nodes per thread; the six populations that move in y are re-aligned across the warp with shuffles so
+//            that all but two stores per warp and plane are 16-byte aligned vector stores.
+#include "ctx.h"
+#include "d2q9.cuh"
+
+namespace life {
+
+struct BulkArgs {
+	const double *fin;
+	double *fout;
+	Layout L;
+	double omega;
+	double fup_x, fup_y;    // uniform force_xy entering u_n   (previous step's value)
+	double fuc_x, fuc_y;    // uniform force_xy of this step   (collision)
+	const double *fibm;     // IBM force planes or nullptr
+	// generic path only
+	const double *macro;    // stored rho_n, ux_n, uy_n planes (first step after an upload) or nullptr
+	double *fxyf;           // force_xy field planes or nullptr
+	int wom_field;          // recompute the force_xy field from rho_n (Womersley with gravity, src/Grid.cpp:55-61)
+	double Drho, gx, gy, dpdx_cos, dpdy_cos, sq, Dm;
+	int64_t c_first;
+	int64_t tiles;          // thread blocks per column
+};
+
+// mode bits of the specialised kernels
+enum { M_NONE = 0, M_UNI = 1, M_IBM = 2, M_UNI_IBM = 3, M_GENERIC = 4 };
+
+// start-of-step macroscopics + collision of one node held in registers
+template <int COLL, int MODE>
+__device__ __forceinline__ void node_update(const BulkArgs &a, int64_t idx, const double (&f)[NV], double (&o)[NV]) {
+	double sum, mx, my;
+	moments(f, sum, mx, my);
+	double Fux = 0.0, Fuy = 0.0, Fcx = 0.0, Fcy = 0.0;   // force entering u_n / force of the collision
+	double rho = sum, ux, uy;
+	if (MODE == M_GENERIC) {
+		double fix = 0.0, fiy = 0.0;
+		if (a.fibm) { fix = a.fibm[idx]; fiy = a.fibm[a.L.S + idx]; }
+		double fpx = a.fup_x, fpy = a.fup_y, fcx = a.fuc_x, fcy = a.fuc_y;
+		if (a.fxyf) { fpx = a.fxyf[idx]; fpy = a.fxyf[a.L.S + idx]; fcx = fpx; fcy = fpy; }
+		if (a.macro) {
+			rho = a.macro[idx]; ux = a.macro[a.L.S + idx]; uy = a.macro[2 * a.L.S + idx];
+		} else {
+			const double inv = 1.0 / rho;
+			ux = (mx + 0.5 * (fpx + fix)) * inv;
+			uy = (my + 0.5 * (fpy + fiy)) * inv;
+		}
+		if (a.wom_field) {
+			fcx = (rho * a.Drho * a.gx + a.dpdx_cos) * a.sq / a.Dm;
+			fcy = (rho * a.Drho * a.gy + a.dpdy_cos) * a.sq / a.Dm;
+			a.fxyf[idx] = fcx;
+			a.fxyf[a.L.S + idx] = fcy;
+		}
+		Fcx = fcx + fix; Fcy = fcy + fiy;
+	} else {
+		if (MODE & M_UNI) { Fux = a.fup_x; Fuy = a.fup_y; Fcx = a.fuc_x; Fcy = a.fuc_y; }
+		if (MODE & M_IBM) {
+			const double fix = a.fibm[idx], fiy = a.fibm[a.L.S + idx];
+			Fux += fix; Fuy += fiy; Fcx += fix; Fcy += fiy;
+		}
+		const double inv = 1.0 / rho;
+		if (MODE == M_NONE) { ux = mx * inv; uy = my * inv; }
+		else { ux = (mx + 0.5 * Fux) * inv; uy = (my + 0.5 * Fuy) * inv; }
+	}
+	constexpr bool HASF = MODE != M_NONE;
+	if (COLL == COLL_CM) collide_cm<HASF>(f, sum, mx, my, rho, ux, uy, Fcx, Fcy, a.omega, o);
+	else collide_bgk<HASF>(f, rho, ux, uy, Fcx, Fcy, a.omega, o);
+}
+
+// ---- DIRECT: one node per thread ------------------------------------------------------------------------------------------
+template <int COLL, int MODE>
+__global__ void __launch_bounds__(256) k_bulk_direct(const BulkArgs a) {
+	const int64_t col = a.c_first + blockIdx.x / a.tiles;
+	const int64_t j = (int64_t)(blockIdx.x % a.tiles) * blockDim.x + threadIdx.x;
+	if (j >= a.L.Ny) return;
+	const int64_t idx = col * a.L.P + j + JOFF;
+	double f[NV], o[NV];
+#pragma unroll
+	for (int v = 0; v < NV; v++) f[v] = __ldg(a.fin + v * a.L.S + idx);
+	node_update<COLL, MODE>(a, idx, f, o);
+#pragma unroll
+	for (int v = 0; v < NV; v++) a.fout[v * a.L.S + idx + LIFE_CX(v) * a.L.P + LIFE_CY(v)] = o[v];
+}
+
+// ---- SHUFFLE: two nodes per thread, warp-shuffle realignment of the y-moving populations -------------------------------------
+// A warp owns 64 consecutive rows R..R+63 (R even) of one column.  Thread `lane` holds rows R+2*lane and R+2*lane+1.
+// Population with cy = +1: row q goes to row q+1.  The aligned pair (R+2l, R+2l+1) of the destination therefore consists of
+// the upper element of lane l-1 and the lower element of lane l: one shuffle-up, then lanes 1..31 issue one aligned 16-byte
+// store each; lane 0 stores row R+1 alone and lane 31 stores row R+64 alone.  cy = -1 is the mirror image (shuffle-down).
+template <int COLL, int MODE>
+__global__ void __launch_bounds__(256) k_bulk_shuffle(const BulkArgs a) {
+	const int64_t col = a.c_first + blockIdx.x / a.tiles;
+	const int64_t j = ((int64_t)(blockIdx.x % a.tiles) * blockDim.x + threadIdx.x) * 2;
+	const int lane = threadIdx.x & 31;
+	const bool v0ok = j < a.L.Ny, v1ok = j + 1 < a.L.Ny;
+	// whole warps beyond the column exit together (Ny tail): shuffles below need converged warps only among survivors
+	const int64_t jw = j - 2 * lane;
+	if (jw >= a.L.Ny) return;
+	const int64_t idx = col * a.L.P + j + JOFF;   // even → 16-byte aligned
+	double f0[NV], f1[NV], o0[NV], o1[NV];
+#pragma unroll
+	for (int v = 0; v < NV; v++) {
+		// rows beyond Ny still lie inside the padded pitch (ghost row + padding), so the vector load is always in bounds
+		const double2 t = __ldg(reinterpret_cast<const double2 *>(a.fin + v * a.L.S + idx));
+		f0[v] = t.x; f1[v] = t.y;
+	}
+	if (v0ok) node_update<COLL, MODE>(a, idx, f0, o0);
+	if (v1ok) node_update<COLL, MODE>(a, idx + 1, f1, o1);
+#pragma unroll
+	for (int v = 0; v < NV; v++) {
+		double *dst = a.fout + v * a.L.S + idx + LIFE_CX(v) * a.L.P;
+		if (LIFE_CY(v) == 0) {
+			if (v1ok) *reinterpret_cast<double2 *>(dst) = make_double2(o0[v], o1[v]);
+			else if (v0ok) dst[0] = o0[v];
+		} else if (LIFE_CY(v) == 1) {
+			// destination rows j+1, j+2.  aligned pair (j, j+1) = { upper of lane-1 , own lower }
+			const double up = __shfl_up_sync(0xffffffffu, o1[v], 1);
+			if (lane == 0) { if (v0ok) dst[1] = o0[v]; }
+			else if (v0ok) *reinterpret_cast<double2 *>(dst) = make_double2(up, o0[v]);
+			else if (j - 1 < a.L.Ny) dst[0] = up;            // first thread past the end still owns row j (= upper of lane-1)
+			if (lane == 31 && v1ok) dst[2] = o1[v];
+		} else {
+			// destination rows j-1, j.  aligned pair (j, j+1) = { own upper , lower of lane+1 }
+			const double dn = __shfl_down_sync(0xffffffffu, o0[v], 1);
+			if (lane == 0 && v0ok) dst[-1] = o0[v];
+			if (lane == 31) { if (v1ok) dst[0] = o1[v]; }
+			else if (j + 2 < a.L.Ny) { *reinterpret_cast<double2 *>(dst) = make_double2(o1[v], dn); }
+			else if (v1ok) dst[0] = o1[v];
+		}
+	}
+}
+
+template <int COLL, int MODE>
+static int launch_one(life_ctx *ctx, const BulkArgs &a0, int64_t c_count, cudaStream_t st) {
+	BulkArgs a = a0;
+	const int threads = 256;
+	const bool staged = ctx->cfg.kernel != LIFE_KERNEL_DIRECT;   // AUTO → SHUFFLE
+	const int64_t rows_per_block = staged ? 2 * threads : threads;
+	a.tiles = (a.L.Ny + rows_per_block - 1) / rows_per_block;
+	const int64_t blocks = a.tiles * c_count;
+	if (blocks <= 0) return LIFE_OK;
+	if (blocks > 0x7fffffffLL) return fail(ctx, LIFE_E_ARG, "bulk sweep: grid too large");
+	if (staged) k_bulk_shuffle<COLL, MODE><<<(unsigned)blocks, threads, 0, st>>>(a);
+	else k_bulk_direct<COLL, MODE><<<(unsigned)blocks, threads, 0, st>>>(a);
+	ctx->launches++;
+	LIFE_CUDA(ctx, cudaGetLastError());
+	return LIFE_OK;
+}
+
+template <int COLL>
+static int launch_coll(life_ctx *ctx, const BulkArgs &a, int mode, int64_t c_count, cudaStream_t st) {
+	switch (mode) {
+	case M_NONE: return launch_one<COLL, M_NONE>(ctx, a, c_count, st);
+	case M_UNI: return launch_one<COLL, M_UNI>(ctx, a, c_count, st);
+	case M_IBM: return launch_one<COLL, M_IBM>(ctx, a, c_count, st);
+	case M_UNI_IBM: return launch_one<COLL, M_UNI_IBM>(ctx, a, c_count, st);
+	default: return launch_one<COLL, M_GENERIC>(ctx, a, c_count, st);
+	}
+}
+
+// Sweep local columns [c_first, c_first + c_count) (c = i_local + 1) from ctx->fA into ctx->fB.
+int launch_bulk(life_ctx *ctx, const StepScalars &sc, int64_t c_first, int64_t c_count, cudaStream_t st) {
+	BulkArgs a{};
+	a.fin = ctx->fA;
+	a.fout = ctx->fB;
+	a.L = ctx->L;
+	a.omega = ctx->cfg.omega;
+	a.fup_x = sc.fxy_prev[0]; a.fup_y = sc.fxy_prev[1];
+	a.fuc_x = sc.fxy_cur[0]; a.fuc_y = sc.fxy_cur[1];
+	a.fibm = ctx->fibm_any ? ctx->fibm : nullptr;
+	a.c_first = c_first;
+	const bool generic = ctx->stored_macro_valid || ctx->fxy_mode == FXY_FIELD;
+	int mode;
+	if (generic) {
+		mode = M_GENERIC;
+		a.macro = ctx->stored_macro_valid ? ctx->macro : nullptr;
+		a.fxyf = ctx->fxy_mode == FXY_FIELD ? ctx->fxyf : nullptr;
+		a.wom_field = ctx->wom_field ? 1 : 0;
+		a.Drho = ctx->cfg.Drho; a.gx = ctx->cfg.gravity_x; a.gy = ctx->cfg.gravity_y;
+		a.dpdx_cos = ctx->cfg.dpdx * sc.wom_cos; a.dpdy_cos = ctx->cfg.dpdy * sc.wom_cos;
+		a.sq = (ctx->cfg.Dx * ctx->cfg.Dt) * (ctx->cfg.Dx * ctx->cfg.Dt);
+		a.Dm = ctx->cfg.Dm;
+	} else {
+		const bool uni = ctx->fxy_mode == FXY_UNIFORM;
+		mode = (uni ? M_UNI : 0) | (a.fibm ? M_IBM : 0);
+	}
+	if (ctx->cfg.collision == LIFE_CENTRAL_MOMENTS) return launch_coll<COLL_CM>(ctx, a, mode, c_count, st);
+	return launch_coll<COLL_BGK>(ctx, a, mode, c_count, st);
+}
+
+}  // namespace life

@@ -1,0 +1,229 @@
+// Host <-> device movement in the reference's layout, and the on-demand macroscopic / max-speed kernels.
+//   upload_field / download_field : AoS host arrays (f[id*9+v], u[id*2+d], rho[id]; id = i*Ny + j, src/Grid.cpp:70)
+//                                   <-> padded SoA planes (ctx.h), staged through a device scratch buffer in column chunks
+//   launch_macro                  : rho, u as GridClass holds them at the end of a step (src/Grid.cpp:282-299 +
+//                                   src/IBMNode.cpp:97-136), evaluated from f and the current forces
+//   launch_max_speed              : the scan of GridClass::writeInfo (src/Grid.cpp:562-588)
+#include "ctx.h"
+#include "d2q9.cuh"
+
+namespace life {
+
+int ensure_scratch(life_ctx *ctx, size_t bytes) {
+	if (ctx->scratch_bytes >= bytes) return LIFE_OK;
+	if (ctx->scratch) cudaFree(ctx->scratch);
+	ctx->scratch = nullptr;
+	ctx->scratch_bytes = 0;
+	LIFE_CUDA(ctx, cudaMalloc(&ctx->scratch, bytes));
+	ctx->scratch_bytes = bytes;
+	return LIFE_OK;
+}
+
+int ensure_macro(life_ctx *ctx) {
+	if (ctx->macro) return LIFE_OK;
+	LIFE_CUDA(ctx, cudaMalloc(&ctx->macro, sizeof(double) * 3 * ctx->L.S));
+	LIFE_CUDA(ctx, cudaMemsetAsync(ctx->macro, 0, sizeof(double) * 3 * ctx->L.S, ctx->stream));
+	return LIFE_OK;
+}
+
+int ensure_fibm(life_ctx *ctx) {
+	if (ctx->fibm) return LIFE_OK;
+	LIFE_CUDA(ctx, cudaMalloc(&ctx->fibm, sizeof(double) * 2 * ctx->L.S));
+	LIFE_CUDA(ctx, cudaMemsetAsync(ctx->fibm, 0, sizeof(double) * 2 * ctx->L.S, ctx->stream));
+	return LIFE_OK;
+}
+
+// AoS chunk (columns il0 .. il0+ncols-1) -> planes.  One thread per (node, component); consecutive threads read
+// consecutive doubles of the AoS chunk.
+__global__ void k_unpack(const double *__restrict__ src, double *__restrict__ planes, Layout L, int ncomp, int64_t il0,
+                         int64_t n_elems) {
+	const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= n_elems) return;
+	const int64_t node = e / ncomp;
+	const int k = (int)(e - node * ncomp);
+	const int64_t il = il0 + node / L.Ny, j = node % L.Ny;
+	planes[k * L.S + L.node(il, j)] = src[e];
+}
+
+__global__ void k_pack(double *__restrict__ dst, const double *__restrict__ planes, Layout L, int ncomp, int64_t il0,
+                       int64_t n_elems) {
+	const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= n_elems) return;
+	const int64_t node = e / ncomp;
+	const int k = (int)(e - node * ncomp);
+	const int64_t il = il0 + node / L.Ny, j = node % L.Ny;
+	dst[e] = planes[k * L.S + L.node(il, j)];
+}
+
+static int64_t chunk_columns(life_ctx *ctx, int ncomp) {
+	const int64_t per_col = ctx->L.Ny * ncomp;
+	const int64_t target = (int64_t)(256ll << 20) / (int64_t)sizeof(double);   // 256 MiB staging
+	int64_t cols = target / per_col;
+	if (cols < 1) cols = 1;
+	if (cols > ctx->L.nxl) cols = ctx->L.nxl;
+	return cols;
+}
+
+int upload_field(life_ctx *ctx, const double *h, double *planes, int ncomp, double) {
+	const Layout &L = ctx->L;
+	const int64_t cols = chunk_columns(ctx, ncomp);
+	int rc = ensure_scratch(ctx, sizeof(double) * (size_t)(cols * L.Ny * ncomp));
+	if (rc) return rc;
+	for (int64_t il0 = 0; il0 < L.nxl; il0 += cols) {
+		const int64_t nc = (il0 + cols <= L.nxl) ? cols : L.nxl - il0;
+		const int64_t n_elems = nc * L.Ny * ncomp;
+		LIFE_CUDA(ctx, cudaMemcpyAsync(ctx->scratch, h + il0 * L.Ny * ncomp, sizeof(double) * n_elems,
+		                               cudaMemcpyHostToDevice, ctx->stream));
+		k_unpack<<<(unsigned)((n_elems + 255) / 256), 256, 0, ctx->stream>>>(ctx->scratch, planes, L, ncomp, il0, n_elems);
+		ctx->launches++;
+		LIFE_CUDA(ctx, cudaGetLastError());
+	}
+	return LIFE_OK;
+}
+
+int download_field(life_ctx *ctx, double *h, const double *planes, int ncomp) {
+	const Layout &L = ctx->L;
+	const int64_t cols = chunk_columns(ctx, ncomp);
+	int rc = ensure_scratch(ctx, sizeof(double) * (size_t)(cols * L.Ny * ncomp));
+	if (rc) return rc;
+	for (int64_t il0 = 0; il0 < L.nxl; il0 += cols) {
+		const int64_t nc = (il0 + cols <= L.nxl) ? cols : L.nxl - il0;
+		const int64_t n_elems = nc * L.Ny * ncomp;
+		k_pack<<<(unsigned)((n_elems + 255) / 256), 256, 0, ctx->stream>>>(ctx->scratch, planes, L, ncomp, il0, n_elems);
+		ctx->launches++;
+		LIFE_CUDA(ctx, cudaGetLastError());
+		LIFE_CUDA(ctx, cudaMemcpyAsync(h + il0 * L.Ny * ncomp, ctx->scratch, sizeof(double) * n_elems,
+		                               cudaMemcpyDeviceToHost, ctx->stream));
+	}
+	LIFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return LIFE_OK;
+}
+
+// ---- end-of-step macroscopics of every node ----------------------------------------------------------------------------------
+struct MacroArgs {
+	const double *f;
+	Layout L;
+	int fxy_mode;
+	double fx, fy;
+	const double *fxyf, *fibm;
+};
+
+__device__ __forceinline__ void node_macro(const MacroArgs &a, int64_t idx, double &rho, double &ux, double &uy) {
+	double p[NV], mx, my;
+#pragma unroll
+	for (int v = 0; v < NV; v++) p[v] = __ldg(a.f + v * a.L.S + idx);
+	moments(p, rho, mx, my);
+	double fx = a.fx, fy = a.fy;
+	if (a.fxy_mode == FXY_FIELD) { fx = a.fxyf[idx]; fy = a.fxyf[a.L.S + idx]; }
+	if (a.fibm) {
+		// (F_xy + F_ibm)/2 as src/IBMNode.cpp:121-122; off-support F_ibm = 0 and this equals src/Grid.cpp:297-298
+		ux = (mx + 0.5 * (fx + a.fibm[idx])) / rho;
+		uy = (my + 0.5 * (fy + a.fibm[a.L.S + idx])) / rho;
+	} else {
+		ux = (mx + 0.5 * fx) / rho;
+		uy = (my + 0.5 * fy) / rho;
+	}
+}
+
+__global__ void __launch_bounds__(256) k_macro(const MacroArgs a, double *out) {
+	const int64_t tiles = (a.L.Ny + blockDim.x - 1) / blockDim.x;
+	const int64_t col = 1 + blockIdx.x / tiles;
+	const int64_t j = (int64_t)(blockIdx.x % tiles) * blockDim.x + threadIdx.x;
+	if (j >= a.L.Ny) return;
+	const int64_t idx = col * a.L.P + j + JOFF;
+	double rho, ux, uy;
+	node_macro(a, idx, rho, ux, uy);
+	out[idx] = rho;
+	out[a.L.S + idx] = ux;
+	out[2 * a.L.S + idx] = uy;
+}
+
+static MacroArgs macro_args(life_ctx *ctx) {
+	MacroArgs a{};
+	a.f = ctx->fA;
+	a.L = ctx->L;
+	a.fxy_mode = ctx->fxy_mode;
+	a.fx = ctx->fxy_uniform[0]; a.fy = ctx->fxy_uniform[1];
+	a.fxyf = ctx->fxyf;
+	a.fibm = ctx->fibm_any ? ctx->fibm : nullptr;
+	return a;
+}
+
+int launch_macro(life_ctx *ctx, double *out_planes) {
+	MacroArgs a = macro_args(ctx);
+	const int64_t tiles = (a.L.Ny + 255) / 256;
+	const int64_t blocks = tiles * a.L.nxl;
+	k_macro<<<(unsigned)blocks, 256, 0, ctx->stream>>>(a, out_planes);
+	ctx->launches++;
+	LIFE_CUDA(ctx, cudaGetLastError());
+	return LIFE_OK;
+}
+
+// ---- max |u| and NaN scan (src/Grid.cpp:562-588) -------------------------------------------------------------------------------
+// red[0] = bits of the maximum speed (non-negative doubles order like unsigned integers), red[1] = smallest global node id
+// holding a NaN speed (i-major order = the order the reference's double loop meets them), ~0 if none.
+__global__ void __launch_bounds__(256) k_max_speed(const MacroArgs a, const double *stored, int64_t i_begin,
+                                                   unsigned long long *red) {
+	__shared__ unsigned long long smax[256], snan[256];
+	const int64_t n = a.L.nxl * a.L.Ny;
+	unsigned long long vmax = 0ull, nanid = ~0ull;
+	for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+		const int64_t il = k / a.L.Ny, j = k - il * a.L.Ny;
+		const int64_t idx = a.L.node(il, j);
+		double rho, ux, uy;
+		if (stored) { ux = stored[a.L.S + idx]; uy = stored[2 * a.L.S + idx]; }
+		else node_macro(a, idx, rho, ux, uy);
+		const double vel = sqrt(ux * ux + uy * uy);
+		if (vel != vel) {
+			const unsigned long long gid = (unsigned long long)((i_begin + il) * a.L.Ny + j);
+			if (gid < nanid) nanid = gid;
+		} else {
+			const unsigned long long b = (unsigned long long)__double_as_longlong(vel);
+			if (b > vmax) vmax = b;
+		}
+	}
+	smax[threadIdx.x] = vmax; snan[threadIdx.x] = nanid;
+	__syncthreads();
+	for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+		if ((int)threadIdx.x < s) {
+			if (smax[threadIdx.x + s] > smax[threadIdx.x]) smax[threadIdx.x] = smax[threadIdx.x + s];
+			if (snan[threadIdx.x + s] < snan[threadIdx.x]) snan[threadIdx.x] = snan[threadIdx.x + s];
+		}
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) {
+		atomicMax(&red[0], smax[0]);
+		atomicMin(&red[1], snan[0]);
+	}
+}
+
+int launch_max_speed(life_ctx *ctx, double *vmax, int32_t *has_nan, int64_t *nan_id) {
+	if (!ctx->d_red) LIFE_CUDA(ctx, cudaMalloc(&ctx->d_red, 64));
+	unsigned long long init[2] = {0ull, ~0ull};
+	LIFE_CUDA(ctx, cudaMemcpyAsync(ctx->d_red, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+	MacroArgs a = macro_args(ctx);
+	const int64_t n = a.L.nxl * a.L.Ny;
+	int64_t blocks = (n + 255) / 256;
+	if (blocks > 148 * 8) blocks = 148 * 8;
+	k_max_speed<<<(unsigned)blocks, 256, 0, ctx->stream>>>(a, ctx->stored_macro_valid ? ctx->macro : nullptr, ctx->i_begin,
+	                                                      reinterpret_cast<unsigned long long *>(ctx->d_red));
+	ctx->launches++;
+	LIFE_CUDA(ctx, cudaGetLastError());
+	if (ctx->comm) {
+		LIFE_NCCL(ctx, ncclGroupStart());
+		LIFE_NCCL(ctx, ncclAllReduce(ctx->d_red, ctx->d_red, 1, ncclDouble, ncclMax, ctx->comm, ctx->stream));
+		LIFE_NCCL(ctx, ncclAllReduce(ctx->d_red + 1, ctx->d_red + 1, 1, ncclUint64, ncclMin, ctx->comm, ctx->stream));
+		LIFE_NCCL(ctx, ncclGroupEnd());
+	}
+	unsigned long long out[2];
+	LIFE_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_red, sizeof(out), cudaMemcpyDeviceToHost, ctx->stream));
+	LIFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	double v;
+	memcpy(&v, &out[0], sizeof(double));
+	*vmax = v;
+	*has_nan = out[1] != ~0ull;
+	*nan_id = *has_nan ? (int64_t)out[1] : -1;
+	return LIFE_OK;
+}
+
+}  // namespace life

@@ -214,11 +214,9 @@ def run_gpu_arm(args):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from life_b200 import capi
+    from life_b200 import capi, dist as D
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    rank, world, local = D.env_ranks()
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             # plain `python bench.py --gpus N`: re-launch under torchrun, one rank per GPU
@@ -233,11 +231,7 @@ def run_gpu_arm(args):
     nccl_id = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-        buf = torch.zeros(128, dtype=torch.uint8, device=dev)
-        if rank == 0:
-            buf.copy_(torch.frombuffer(bytearray(capi.nccl_unique_id()), dtype=torch.uint8))
-        dist.broadcast(buf, 0)
-        nccl_id = bytes(buf.cpu().numpy().tobytes())
+        nccl_id = D.share_nccl_id()
 
     S, K, W = args.size, args.steps, args.warmup
     Nx, Ny = S * world, S
@@ -272,11 +266,7 @@ def run_gpu_arm(args):
         torch.cuda.synchronize()
 
     def reduce_max(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return D.max_over_ranks(x, device=dev)
 
     # ---- device-resident throughput ("value") ------------------------------------------------------------------------
     ctx.upload_state(h_f, None, None, None, None, u_in, None)
@@ -405,7 +395,7 @@ def main():
     if args.impl == "reference":
         return run_reference_arm(args)
     if args.steps is None:
-        args.steps = 200
+        args.steps = 500
     args.warmup = max(args.warmup, 3)
     return run_gpu_arm(args)
 

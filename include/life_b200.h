@@ -110,6 +110,11 @@ const char *life_last_error(const life_ctx *ctx);
 /* Columns [*i_begin, *i_end) of the global lattice owned by this context. */
 int life_slab(const life_ctx *ctx, int64_t *i_begin, int64_t *i_end);
 
+/* The same partition without a context (pure arithmetic, usable before any device exists): the balanced split of Nx
+ * columns over nranks slabs, the first Nx % nranks slabs one column wider.  The host uses it to cut the global
+ * reference arrays (contiguous in x, src/Grid.cpp:70) into the per-rank chunks life_upload_state expects. */
+int life_slab_range(int64_t Nx, int32_t nranks, int32_t rank, int64_t *i_begin, int64_t *i_end);
+
 /* ---- state in / out --------------------------------------------------------------------------------------------- */
 
 /*

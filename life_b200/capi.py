@@ -21,6 +21,7 @@ OK, E_ARG, E_CUDA, E_NCCL, E_STATE, E_SUPPORT, E_NOMEM = range(7)
 # every symbol include/life_b200.h declares (tests check the library exports exactly these)
 EXPORTS = [
     "life_abi_version", "life_nccl_unique_id", "life_create", "life_destroy", "life_last_error", "life_slab",
+    "life_slab_range",
     "life_upload_state", "life_download_macro", "life_download_state", "life_max_speed", "life_step", "life_step_n",
     "life_sync", "life_ibm_set_markers", "life_ibm_interp", "life_ibm_spread", "life_ibm_set_forces",
     "life_ibm_get_interp", "life_ibm_get_supports", "life_get_boundary", "life_get_types", "life_launch_count",
@@ -85,6 +86,7 @@ def load():
     L.life_last_error.restype = C.c_char_p
     L.life_last_error.argtypes = [vp]
     L.life_slab.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
+    L.life_slab_range.argtypes = [i64, i32, i32, C.POINTER(i64), C.POINTER(i64)]
     L.life_upload_state.argtypes = [vp] + [vp] * 7
     L.life_download_macro.argtypes = [vp, vp, vp]
     L.life_download_state.argtypes = [vp, vp, vp, vp, vp]
@@ -114,6 +116,15 @@ def nccl_unique_id():
     if rc:
         raise LifeError(rc, load().life_last_error(None).decode())
     return bytes(buf)
+
+
+def slab_range(Nx, nranks, rank):
+    """Columns [begin, end) of rank `rank` (life_slab_range: pure arithmetic, no device needed)."""
+    b, e = C.c_int64(), C.c_int64()
+    rc = load().life_slab_range(int(Nx), int(nranks), int(rank), C.byref(b), C.byref(e))
+    if rc:
+        raise LifeError(rc, "life_slab_range: bad arguments")
+    return b.value, e.value
 
 
 def _ptr(a):

@@ -124,9 +124,7 @@ int life_create(const life_config *cfg, life_ctx **out) {
 	ctx->device = dev;
 
 	// slab of columns owned by this rank: balanced split of Nx
-	const int64_t base = cfg->Nx / nranks, rem = cfg->Nx % nranks;
-	ctx->i_begin = rank * base + (rank < rem ? rank : rem);
-	ctx->i_end = ctx->i_begin + base + (rank < rem ? 1 : 0);
+	life_slab_range(cfg->Nx, nranks, rank, &ctx->i_begin, &ctx->i_end);
 	Layout &L = ctx->L;
 	L.Ny = cfg->Ny;
 	L.nxl = ctx->i_end - ctx->i_begin;
@@ -184,6 +182,16 @@ int life_create(const life_config *cfg, life_ctx **out) {
 
 int life_destroy(life_ctx *ctx) {
 	free_ctx(ctx);
+	return LIFE_OK;
+}
+
+int life_slab_range(int64_t Nx, int32_t nranks, int32_t rank, int64_t *i_begin, int64_t *i_end) {
+	if (nranks < 1) nranks = 1;
+	if (Nx < 0 || rank < 0 || rank >= nranks) return LIFE_E_ARG;
+	const int64_t base = Nx / nranks, rem = Nx % nranks;
+	const int64_t b = rank * base + (rank < rem ? rank : rem);
+	if (i_begin) *i_begin = b;
+	if (i_end) *i_end = b + base + (rank < rem ? 1 : 0);
 	return LIFE_OK;
 }
 

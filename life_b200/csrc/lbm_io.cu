@@ -162,24 +162,53 @@ int launch_macro(life_ctx *ctx, double *out_planes) {
 // ---- max |u| and NaN scan (src/Grid.cpp:562-588) -------------------------------------------------------------------------------
 // red[0] = bits of the maximum speed (non-negative doubles order like unsigned integers), red[1] = smallest global node id
 // holding a NaN speed (i-major order = the order the reference's double loop meets them), ~0 if none.
+// Persistent blocks stride over (column, 512-row tile) pairs; each thread handles two adjacent rows with 16-byte loads, like the
+// bulk sweep, so the scan runs at the HBM rate of its 72 B per node.
 __global__ void __launch_bounds__(256) k_max_speed(const MacroArgs a, const double *stored, int64_t i_begin,
                                                    unsigned long long *red) {
 	__shared__ unsigned long long smax[256], snan[256];
-	const int64_t n = a.L.nxl * a.L.Ny;
+	const int64_t tiles = (a.L.Ny + 511) / 512;
+	const int64_t n_tiles = tiles * a.L.nxl;
 	unsigned long long vmax = 0ull, nanid = ~0ull;
-	for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
-		const int64_t il = k / a.L.Ny, j = k - il * a.L.Ny;
-		const int64_t idx = a.L.node(il, j);
-		double rho, ux, uy;
-		if (stored) { ux = stored[a.L.S + idx]; uy = stored[2 * a.L.S + idx]; }
-		else node_macro(a, idx, rho, ux, uy);
-		const double vel = sqrt(ux * ux + uy * uy);
-		if (vel != vel) {
-			const unsigned long long gid = (unsigned long long)((i_begin + il) * a.L.Ny + j);
-			if (gid < nanid) nanid = gid;
+	for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+		const int64_t il = tile / tiles;
+		const int64_t j = ((tile - il * tiles) * 256 + threadIdx.x) * 2;
+		if (j >= a.L.Ny) continue;
+		const int64_t idx = a.L.node(il, j);      // even row offset: 16-byte aligned
+		const bool two = j + 1 < a.L.Ny;
+		double ux[2], uy[2];
+		if (stored) {
+			ux[0] = stored[a.L.S + idx]; uy[0] = stored[2 * a.L.S + idx];
+			ux[1] = two ? stored[a.L.S + idx + 1] : 0.0; uy[1] = two ? stored[2 * a.L.S + idx + 1] : 0.0;
+		} else if (a.fxy_mode == FXY_FIELD || a.fibm) {
+			double rho;
+			node_macro(a, idx, rho, ux[0], uy[0]);
+			if (two) node_macro(a, idx + 1, rho, ux[1], uy[1]);
+			else { ux[1] = 0.0; uy[1] = 0.0; }
 		} else {
-			const unsigned long long b = (unsigned long long)__double_as_longlong(vel);
-			if (b > vmax) vmax = b;
+			double p0[NV], p1[NV];
+#pragma unroll
+			for (int v = 0; v < NV; v++) {
+				// the row after the last one is the ghost row: inside the padded pitch, never out of bounds
+				const double2 t = __ldg(reinterpret_cast<const double2 *>(a.f + v * a.L.S + idx));
+				p0[v] = t.x; p1[v] = t.y;
+			}
+			double rho, mx, my;
+			moments(p0, rho, mx, my);
+			ux[0] = (mx + 0.5 * a.fx) / rho; uy[0] = (my + 0.5 * a.fy) / rho;
+			moments(p1, rho, mx, my);
+			ux[1] = two ? (mx + 0.5 * a.fx) / rho : 0.0; uy[1] = two ? (my + 0.5 * a.fy) / rho : 0.0;
+		}
+#pragma unroll
+		for (int k = 0; k < 2; k++) {
+			const double vel = sqrt(ux[k] * ux[k] + uy[k] * uy[k]);
+			if (vel != vel) {
+				const unsigned long long gid = (unsigned long long)((i_begin + il) * a.L.Ny + j + k);
+				if (gid < nanid) nanid = gid;
+			} else {
+				const unsigned long long b = (unsigned long long)__double_as_longlong(vel);
+				if (b > vmax) vmax = b;
+			}
 		}
 	}
 	smax[threadIdx.x] = vmax; snan[threadIdx.x] = nanid;
@@ -202,9 +231,8 @@ int launch_max_speed(life_ctx *ctx, double *vmax, int32_t *has_nan, int64_t *nan
 	unsigned long long init[2] = {0ull, ~0ull};
 	LIFE_CUDA(ctx, cudaMemcpyAsync(ctx->d_red, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
 	MacroArgs a = macro_args(ctx);
-	const int64_t n = a.L.nxl * a.L.Ny;
-	int64_t blocks = (n + 255) / 256;
-	if (blocks > 148 * 8) blocks = 148 * 8;
+	int64_t blocks = ((a.L.Ny + 511) / 512) * a.L.nxl;
+	if (blocks > 148 * 8) blocks = 148 * 8;      // persistent: 8 resident blocks per SM
 	k_max_speed<<<(unsigned)blocks, 256, 0, ctx->stream>>>(a, ctx->stored_macro_valid ? ctx->macro : nullptr, ctx->i_begin,
 	                                                      reinterpret_cast<unsigned long long *>(ctx->d_red));
 	ctx->launches++;

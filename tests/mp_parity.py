@@ -1,0 +1,103 @@
+"""Multi-GPU parity worker (run under torchrun by tests/test_gpu_multi.py, one rank per GPU):
+
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port P tests/mp_parity.py CASE [STEPS]
+
+Every rank builds the oracle's whole-lattice state (deterministic), takes its x-slab, steps it through the C ABI with the
+NCCL halo exchange, and compares its slab with the oracle's whole-lattice result: fields and marker forces within relative
+L2 1e-10.  For cases with bodies the recorded call-site trace of the compiled reference (tests/golden) drives the markers.
+Exit code 0 = parity on every rank.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    from life_b200 import capi, dist as D
+    from tests import cases as K
+
+    case = sys.argv[1]
+    rank, world, local = D.env_ranks()
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    nid = D.share_nccl_id()
+
+    g = K.golden(case)
+    steps = int(sys.argv[2]) if len(sys.argv) > 2 else int(g["steps"])
+    o = K.make_oracle(g)
+    cfg = K.life_config(o.params, o, rank=rank, nranks=world, device=local)
+    ctx = capi.Context(cfg, nccl_id=nid)
+    Nx = o.Nx
+    b, e = ctx.i_begin, ctx.i_end
+    assert (b, e) == capi.slab_range(Nx, world, rank)
+    sl = lambda name: D.slab_of(o.get(name), Nx, rank, world)
+    ctx.upload_state(sl("f"), sl("rho"), sl("u"), sl("force_xy"), sl("force_ibm"), o.get("u_in"), o.get("rho_in"))
+
+    has_ibm = "trace_step" in g.files
+    worst_force = 0.0
+    if has_ibm:
+        k = 0
+        for t in range(1, steps + 1):
+            ctx.step(t)
+            while True:
+                assert g["trace_step"][k] == t
+                ctx.ibm_set_markers(g["trace_pos"][k], g["trace_vel"][k], g["trace_ds"][k], g["trace_eps"][k])
+                force = ctx.ibm_interp()
+                worst_force = max(worst_force, K.rel_l2(force, g["trace_force"][k], floor=1e-6))
+                last = g["trace_last"][k]
+                k += 1
+                if last:
+                    break
+            ctx.ibm_spread()
+    else:
+        for t in range(1, steps + 1):
+            ctx.step(t)
+        o.step(steps)
+    vmax, has_nan, _, _ = ctx.max_speed()
+    st = ctx.download_state()
+    ctx.close()
+
+    ok = True
+    msgs = []
+    if has_ibm:
+        if not worst_force < K.TOL:
+            ok = False
+            msgs.append("marker force %.3e" % worst_force)
+        # golden fixture: sampled nodes of the compiled reference's final state; compare those that fall in this slab
+        s = g["sample"]
+        i, j = s // int(g["Ny"]), s % int(g["Ny"])
+        m = (i >= b) & (i < e)
+        for name in ("rho", "u", "f", "force_ibm"):
+            if m.any():
+                err = K.rel_l2(st[name][i[m] - b, j[m]], g[name][m], floor=1e-12 if name == "force_ibm" else 0.0)
+                if not err < K.TOL:
+                    ok = False
+                    msgs.append("%s %.3e" % (name, err))
+    else:
+        for name in ("rho", "u", "f"):
+            # a slab can lie where the flow has not arrived yet (ChannelFlow's outlet half): u there is rounding noise of
+            # the O(1) populations, so the denominator is floored at 1e-6 per entry (error bar 1e-16 absolute)
+            err = K.rel_l2(st[name], o.get(name)[b:e], floor=1e-6 if name == "u" else 0.0)
+            if not err < K.TOL:
+                ok = False
+                msgs.append("%s %.3e" % (name, err))
+        u = o.get("u")
+        want = np.sqrt((u ** 2).sum(axis=-1)).max()
+        if has_nan or abs(vmax - want) > 1e-12:
+            ok = False
+            msgs.append("max speed %r vs %r" % (vmax, want))
+    flag = torch.tensor([0 if ok else 1], device="cuda")
+    dist.all_reduce(flag)
+    print("[rank %d/%d] %s columns [%d,%d): %s" % (rank, world, case, b, e, "ok" if ok else "MISMATCH " + "; ".join(msgs)), flush=True)
+    dist.destroy_process_group()
+    return int(flag.item() != 0)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

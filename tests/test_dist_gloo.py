@@ -1,0 +1,139 @@
+"""Multi-rank host logic on CPU: torch.distributed with the gloo backend, world_size 2 and 3.
+
+The GPU data path (csrc/halo.cu over NCCL) cannot run here; what can be checked without a GPU is everything around it:
+  * the slab partition (life_slab_range) and the scatter / gather of reference-layout arrays (life_b200/dist.py),
+  * the rendezvous of the ncclUniqueId,
+  * the halo DESIGN: a numpy model of "push into a ghost ring, ship the three outgoing populations of one column per face
+    to the neighbour, wrap y locally" — executed by real ranks exchanging real messages over gloo — lands every population
+    exactly where the reference's push map recv = ((i+cx+Nx)%Nx)*Ny + (j+cy+Ny)%Ny (src/Grid.cpp:229,240) sends it.
+"""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CX = [0, 1, -1, 0, 0, 1, -1, 1, -1]
+CY = [0, 0, 0, 1, -1, 1, -1, -1, 1]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, Nx, Ny, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from life_b200 import capi, dist as D
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        # --- rendezvous of the communicator id (any 128 bytes will do on CPU)
+        nid = D.share_nccl_id(make_id=lambda: bytes(range(128)))
+        assert nid == bytes(range(128))
+
+        # --- scatter / gather in the reference layout
+        tags = np.arange(1, Nx * Ny * 9 + 1, dtype=np.float64).reshape(Nx, Ny, 9) if rank == 0 else None
+        mine = D.scatter_slabs(tags, Nx)
+        b, e = capi.slab_range(Nx, world, rank)
+        assert mine.shape == (e - b, Ny, 9)
+        assert mine[0, 0, 0] == b * Ny * 9 + 1
+        back = D.gather_slabs(mine, Nx)
+        if rank == 0:
+            assert np.array_equal(back, tags)
+        assert D.max_over_ranks(float(rank)) == world - 1
+
+        # --- the halo design, executed: local push into a ghost ring, exchange per halo_plan, wrap y
+        nxl = e - b
+        ring = np.zeros((9, nxl + 2, Ny + 2))              # [v, c = il + 1, r = j + 1]
+        for v in range(9):
+            ring[v, 1 + CX[v]:1 + CX[v] + nxl, 1 + CY[v]:1 + CY[v] + Ny] = mine[:, :, v]
+        # y wrap of every column incl. ghosts (periodic top/bottom: what k_wrap_y does before the exchange)
+        for v in range(9):
+            if CY[v] == 1:
+                ring[v, :, 1] = ring[v, :, Ny + 1]
+            elif CY[v] == -1:
+                ring[v, :, Ny] = ring[v, :, 0]
+        plan = D.halo_plan(Nx, Ny, world, periodic_x=True)
+        sends = [p for p in plan if p[0] == rank]
+        recvs = [p for p in plan if p[1] == rank]
+        reqs, bufs = [], []
+        for (_, dst, pops, n) in sends:
+            col = nxl + 1 if pops == (1, 5, 7) else 0
+            msg = torch.from_numpy(np.ascontiguousarray(np.stack([ring[v, col, 1:Ny + 1] for v in pops])))
+            assert msg.numel() == n
+            reqs.append(dist.isend(msg, dst=dst, tag=0 if pops == (1, 5, 7) else 1))
+        for (src, _, pops, n) in recvs:
+            buf = torch.empty((3, Ny), dtype=torch.float64)
+            reqs.append(dist.irecv(buf, src=src, tag=0 if pops == (1, 5, 7) else 1))
+            bufs.append((pops, buf))
+        for q in reqs:
+            q.wait()
+        for pops, buf in bufs:
+            col = 1 if pops == (1, 5, 7) else nxl            # cx=+1 arrive in my first column, cx=-1 in my last
+            for k, v in enumerate(pops):
+                ring[v, col, 1:Ny + 1] = buf[k].numpy()
+        got = np.ascontiguousarray(np.transpose(ring[:, 1:nxl + 1, 1:Ny + 1], (1, 2, 0)))
+        full = D.gather_slabs(got, Nx)
+        if rank == 0:
+            expect = np.zeros_like(tags)
+            i, j = np.meshgrid(np.arange(Nx), np.arange(Ny), indexing="ij")
+            for v in range(9):
+                expect[(i + CX[v] + Nx) % Nx, (j + CY[v] + Ny) % Ny, v] = tags[i, j, v]
+            assert np.array_equal(full, expect)
+            open(os.path.join(out_dir, "ok"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,shape", [(2, (12, 7)), (3, (13, 5)), (2, (9, 16))])
+def test_slab_plumbing_and_halo_design_over_gloo(world, shape, tmp_path, lib_built):
+    import torch.multiprocessing as mp
+    Nx, Ny = shape
+    mp.spawn(_worker, args=(world, _free_port(), Nx, Ny, str(tmp_path)), nprocs=world, join=True)
+    assert (tmp_path / "ok").exists()
+
+
+def test_slab_partition_covers_the_lattice(lib_built):
+    from life_b200 import capi
+    for Nx in (4, 17, 501, 16384 * 8):
+        for world in (1, 2, 3, 8):
+            edges = [capi.slab_range(Nx, world, r) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == Nx
+            for a, b in zip(edges, edges[1:]):
+                assert a[1] == b[0]
+            widths = [e - b for b, e in edges]
+            assert max(widths) - min(widths) <= 1
+
+
+def test_halo_plan_is_exactly_what_leaves_a_slab():
+    """Against the oracle's restatement of the push map: the only (node, population) pairs whose target lies in another
+    slab are the cx=+1 populations of a slab's last column and the cx=-1 populations of its first column."""
+    from oracle import oracle as O
+    from life_b200 import capi, dist as D
+    Nx, Ny, world = 11, 6, 3
+    o = O.Oracle(O.Params(Nx=Nx, Ny=Ny, wall_left=0, wall_right=0, wall_bottom=0, wall_top=0))
+    owner = np.zeros(Nx, int)
+    for r in range(world):
+        b, e = capi.slab_range(Nx, world, r)
+        owner[b:e] = r
+    crossing = {}
+    for i in range(Nx):
+        for j in range(Ny):
+            for v in range(9):
+                ti = o.stream_target(i, j, v) // Ny
+                if owner[ti] != owner[i]:
+                    crossing.setdefault((owner[i], owner[ti]), set()).add((i, v))
+    plan = D.halo_plan(Nx, Ny, world, periodic_x=True)
+    assert {(s, d) for s, d, _, _ in plan} == set(crossing)
+    for s, d, pops, n in plan:
+        b, e = capi.slab_range(Nx, world, s)
+        col = e - 1 if pops == (1, 5, 7) else b
+        assert crossing[(s, d)] == {(col, v) for v in pops}
+        assert n == 3 * Ny

@@ -1,0 +1,110 @@
+"""The drop-in at program level: LIFE's own main() with the hot path on the B200 (life_b200/host/_build/<case>/LIFE_b200)
+against the unmodified reference program (LIFE_ref, same sources, same case) — the reference's own regression protocol
+(testing/store-ref-data.sh, testing/run-tests.sh: 500 steps, restart every 100, TurekHron run twice to exercise the restart
+path, then compare Results/), with `diff -r` relaxed to the north-star tolerance: fields and marker forces within
+relative L2 1e-10.  The host-side FEM / LAPACK epsilon solve / Aitken loop run live in both programs.
+"""
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests import cases as K
+from tests import restartfile as R
+
+HOST = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "life_b200", "host", "_build")
+EXAMPLES = K.EXAMPLES_LBM + K.EXAMPLES_IBM
+
+
+def _have(case, exe):
+    return os.path.exists(os.path.join(HOST, case, exe))
+
+
+def _run(case, exe, workdir, times=1):
+    os.makedirs(workdir, exist_ok=True)
+    inp = os.path.join(HOST, case, "input")
+    if os.path.isdir(inp):
+        shutil.copytree(inp, os.path.join(workdir, "input"), dirs_exist_ok=True)
+    env = dict(os.environ, OPENBLAS_NUM_THREADS="1")
+    for _ in range(times):
+        p = subprocess.run([os.path.join(HOST, case, exe)], cwd=workdir, env=env, stdout=subprocess.PIPE,
+                           stderr=subprocess.PIPE, text=True, timeout=1200)
+    return p
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", EXAMPLES)
+def test_program_reproduces_reference_results(case, tmp_path):
+    if not (_have(case, "LIFE_b200") and _have(case, "LIFE_ref")):
+        pytest.skip("life_b200/host/_build/%s not built (make -C life_b200/host needs /root/reference)" % case)
+    times = 2 if case == "TurekHron" else 1          # second run restarts from Results/Restart (store-ref-data.sh:51-53)
+    ref = _run(case, "LIFE_ref", str(tmp_path / "ref"), times)
+    assert ref.returncode == 0, ref.stdout[-2000:]
+    new = _run(case, "LIFE_b200", str(tmp_path / "b200"), times)
+    assert new.returncode == 0, new.stdout[-2000:] + new.stderr[-2000:]
+    assert "life_step" in new.stderr and " 0 life_step" not in new.stderr      # the CUDA path really ran
+
+    a = R.read_fluid(str(tmp_path / "ref" / "Results" / "Restart" / "Fluid.restart"))
+    b = R.read_fluid(str(tmp_path / "b200" / "Results" / "Restart" / "Fluid.restart"))
+    assert (a["t"], a["Nx"], a["Ny"]) == (b["t"], b["Nx"], b["Ny"])
+    assert a["t"] == 500 * times
+    for name in ("rho", "u", "f"):
+        err = K.rel_l2(b[name], a[name])
+        assert err < K.TOL, (case, name, err)
+    err = K.rel_l2(b["force_ibm"], a["force_ibm"], floor=1e-12)
+    assert err < K.TOL, (case, "force_ibm", err)
+
+    ibm = tmp_path / "ref" / "Results" / "Restart" / "IBM.restart"
+    if ibm.exists():
+        ma, mb = R.read_ibm(str(ibm)), R.read_ibm(str(tmp_path / "b200" / "Results" / "Restart" / "IBM.restart"))
+        assert len(ma) == len(mb)
+        for x, y in zip(ma, mb):
+            assert x["id"] == y["id"]
+            assert K.rel_l2(y["pos"], x["pos"]) < K.TOL
+            assert K.rel_l2(y["vel"], x["vel"], floor=1e-9) < K.TOL * 100     # velocities of a body at rest are rounding noise
+        fa = np.concatenate([x["force"] for x in ma])
+        fb = np.concatenate([x["force"] for x in mb])
+        assert K.rel_l2(fb, fa, floor=1e-9) < K.TOL, (case, "marker force")
+        ta = R.read_table(str(tmp_path / "ref" / "Results" / "TotalForces.out"))
+        tb = R.read_table(str(tmp_path / "b200" / "Results" / "TotalForces.out"))
+        assert ta.shape == tb.shape
+        assert np.array_equal(ta[:, 0], tb[:, 0])
+        # printed with 10 significant digits (params.h:110)
+        assert K.rel_l2(tb[:, 2:4], ta[:, 2:4]) < 1e-8, (case, "TotalForces.out")
+    # the VTK series written on the way (every nSteps/10) exists in both and the last frame agrees byte for byte in size
+    va = sorted(os.listdir(tmp_path / "ref" / "Results" / "VTK"))
+    vb = sorted(os.listdir(tmp_path / "b200" / "Results" / "VTK"))
+    assert va == vb
+
+
+def test_program_refuses_to_run_without_a_gpu(tmp_path):
+    """No CPU fallback: without a CUDA device the drop-in program stops through the reference's ERROR() (exit 99)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    case = "LidDrivenCavity"
+    if not _have(case, "LIFE_b200"):
+        pytest.skip("life_b200/host/_build not built")
+    p = _run(case, "LIFE_b200", str(tmp_path / "run"))
+    assert p.returncode == 99
+    assert "no CPU path" in p.stdout or "life_create failed" in p.stdout
+
+
+@pytest.mark.parametrize("case", K.EXAMPLES_LBM)
+def test_oracle_matches_the_reference_program(case, tmp_path):
+    """Pins the oracle at whole-program level: 500 steps of the unmodified reference executable (its Fluid.restart) against
+    500 steps of oracle/life_oracle.c from the same initial state."""
+    if not _have(case, "LIFE_ref"):
+        pytest.skip("life_b200/host/_build/%s/LIFE_ref not built" % case)
+    p = _run(case, "LIFE_ref", str(tmp_path / "ref"))
+    assert p.returncode == 0
+    a = R.read_fluid(str(tmp_path / "ref" / "Results" / "Restart" / "Fluid.restart"))
+    g = K.golden(case)
+    assert not int(g["wavy"])
+    o = K.make_oracle(g)
+    o.step(500)
+    for name in ("rho", "u", "f"):
+        err = K.rel_l2(o.get(name), a[name])
+        assert err < 1e-12, (case, name, err)

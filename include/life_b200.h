@@ -87,7 +87,8 @@ typedef struct life_config {
 	int32_t rank, nranks;      /* x-slab decomposition; nranks <= 1: single GPU                                */
 	const void *nccl_id;       /* 128-byte ncclUniqueId shared by all ranks (life_nccl_unique_id); NULL iff nranks <= 1 */
 	int32_t kernel;            /* LIFE_KERNEL_*                                                                 */
-	int32_t reserved[7];
+	int32_t tune;              /* measurement only: launch-shape / cache-hint variant of the bulk sweep, 0 = default (csrc/lbm_bulk.cu) */
+	int32_t reserved[6];
 } life_config;
 
 typedef struct life_ctx life_ctx;
@@ -130,6 +131,22 @@ int life_slab_range(int64_t Nx, int32_t nranks, int32_t rank, int64_t *i_begin, 
  */
 int life_upload_state(life_ctx *ctx, const double *f, const double *rho, const double *u, const double *force_xy,
                       const double *force_ibm, const double *u_in, const double *rho_in);
+
+/*
+ * Streaming form of life_upload_state for lattices whose host image does not fit in host RAM at once, or is read from a
+ * restart file in pieces (readRestart, src/Grid.cpp:1072-1160, reads node by node): the reference's 228 B/node of host
+ * arrays are 59 GB at 16384^2.  life_upload_begin takes the per-lattice inputs and resets the state;
+ * life_upload_columns hands over the same arrays as life_upload_state restricted to LOCAL columns [il0, il0 + ncols) of
+ * this rank's slab (each column exactly once, any order; rho/u either for every range or for none);
+ * life_upload_end completes it.  life_upload_state == begin + columns(0, all) + end.
+ */
+int life_upload_begin(life_ctx *ctx, const double *u_in, const double *rho_in);
+int life_upload_columns(life_ctx *ctx, int64_t il0, int64_t ncols, const double *f, const double *rho, const double *u,
+                        const double *force_xy, const double *force_ibm);
+int life_upload_end(life_ctx *ctx);
+
+/* Streaming form of life_download_state: local columns [il0, il0 + ncols); any pointer may be NULL. */
+int life_download_columns(life_ctx *ctx, int64_t il0, int64_t ncols, double *f, double *rho, double *u, double *force_ibm);
 
 /* rho [n], u [n*2] as GridClass::rho / GridClass::u hold them at the end of a step (either may be NULL).
  * Replaces the reads of writeInfo (src/Grid.cpp:559-588) and writeVTK (src/Grid.cpp:858-889). */

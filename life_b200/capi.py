@@ -22,7 +22,8 @@ OK, E_ARG, E_CUDA, E_NCCL, E_STATE, E_SUPPORT, E_NOMEM = range(7)
 EXPORTS = [
     "life_abi_version", "life_nccl_unique_id", "life_create", "life_destroy", "life_last_error", "life_slab",
     "life_slab_range",
-    "life_upload_state", "life_download_macro", "life_download_state", "life_max_speed", "life_step", "life_step_n",
+    "life_upload_state", "life_upload_begin", "life_upload_columns", "life_upload_end", "life_download_columns",
+    "life_download_macro", "life_download_state", "life_max_speed", "life_step", "life_step_n",
     "life_sync", "life_ibm_set_markers", "life_ibm_interp", "life_ibm_spread", "life_ibm_set_forces",
     "life_ibm_get_interp", "life_ibm_get_supports", "life_get_boundary", "life_get_types", "life_launch_count",
     "life_bulk_kernel_ms", "life_set_profiling",
@@ -44,7 +45,7 @@ class Config(C.Structure):
                 ("stream", C.c_void_p),
                 ("rank", C.c_int32), ("nranks", C.c_int32),
                 ("nccl_id", C.c_void_p),
-                ("kernel", C.c_int32), ("reserved", C.c_int32 * 7)]
+                ("kernel", C.c_int32), ("tune", C.c_int32), ("reserved", C.c_int32 * 6)]
 
     def __init__(self, **kw):
         super().__init__()
@@ -88,6 +89,10 @@ def load():
     L.life_slab.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
     L.life_slab_range.argtypes = [i64, i32, i32, C.POINTER(i64), C.POINTER(i64)]
     L.life_upload_state.argtypes = [vp] + [vp] * 7
+    L.life_upload_begin.argtypes = [vp, vp, vp]
+    L.life_upload_columns.argtypes = [vp, i64, i64] + [vp] * 5
+    L.life_upload_end.argtypes = [vp]
+    L.life_download_columns.argtypes = [vp, i64, i64] + [vp] * 4
     L.life_download_macro.argtypes = [vp, vp, vp]
     L.life_download_state.argtypes = [vp, vp, vp, vp, vp]
     L.life_max_speed.argtypes = [vp, C.POINTER(dbl), C.POINTER(i32), C.POINTER(i64), C.POINTER(i64)]
@@ -178,6 +183,21 @@ class Context:
         n = self.nxl * self.Ny
         assert arrs[0].size == n * 9, "f has the wrong size for this slab"
         self._ck(self.L.life_upload_state(self.h, *[_ptr(a) for a in arrs]))
+
+    def upload_begin(self, u_in=None, rho_in=None):
+        u_in, rho_in = _f64(u_in), _f64(rho_in)
+        self._ck(self.L.life_upload_begin(self.h, _ptr(u_in), _ptr(rho_in)))
+
+    def upload_columns(self, il0, ncols, f, rho=None, u=None, force_xy=None, force_ibm=None):
+        arrs = [_f64(a) for a in (f, rho, u, force_xy, force_ibm)]
+        assert arrs[0].size == ncols * self.Ny * 9, "f has the wrong size for this column range"
+        self._ck(self.L.life_upload_columns(self.h, int(il0), int(ncols), *[_ptr(a) for a in arrs]))
+
+    def upload_end(self):
+        self._ck(self.L.life_upload_end(self.h))
+
+    def download_columns_into(self, il0, ncols, f=None, rho=None, u=None, force_ibm=None):
+        self._ck(self.L.life_download_columns(self.h, int(il0), int(ncols), _ptr(f), _ptr(rho), _ptr(u), _ptr(force_ibm)))
 
     def download_macro(self, rho=True, u=True):
         r = np.empty((self.nxl, self.Ny)) if rho else None

@@ -202,62 +202,30 @@ int life_slab(const life_ctx *ctx, int64_t *i_begin, int64_t *i_end) {
 	return LIFE_OK;
 }
 
-int life_upload_state(life_ctx *ctx, const double *f, const double *rho, const double *u, const double *force_xy,
-                      const double *force_ibm, const double *u_in, const double *rho_in) {
+int life_upload_begin(life_ctx *ctx, const double *u_in, const double *rho_in) {
 	if (!ctx) return LIFE_E_ARG;
-	if (!f) return fail(ctx, LIFE_E_ARG, "life_upload_state: f is required");
-	if ((rho == nullptr) != (u == nullptr)) return fail(ctx, LIFE_E_ARG, "life_upload_state: give both rho and u, or neither");
 	LIFE_CUDA(ctx, cudaSetDevice(ctx->device));
 	const Layout &L = ctx->L;
-	const int64_t n = L.nxl * L.Ny;
-	int rc;
-	if ((rc = upload_field(ctx, f, ctx->fA, 9, 0.0))) return rc;
-	if (rho) {
-		if ((rc = ensure_macro(ctx))) return rc;
-		if ((rc = upload_field(ctx, rho, ctx->macro, 1, 0.0))) return rc;
-		if ((rc = upload_field(ctx, u, ctx->macro + L.S, 2, 0.0))) return rc;
-		ctx->stored_macro_valid = true;
-	} else {
-		ctx->stored_macro_valid = false;
-	}
-
-	// force_xy: none / uniform / field (src/Grid.cpp:1035-1045 makes it uniform; Womersley with gravity makes it a field)
+	ctx->have_state = false;
+	ctx->uploading = true;
+	ctx->up_macro = -1;
+	ctx->up_cols = 0;
+	ctx->up_fxy_seen = false;
+	ctx->up_fxy_uniform = true;
+	ctx->up_fxy0[0] = ctx->up_fxy0[1] = 0.0;
+	ctx->up_ranges.clear();
+	ctx->stored_macro_valid = false;
 	ctx->fxy_mode = FXY_NONE;
 	ctx->fxy_uniform[0] = ctx->fxy_uniform[1] = 0.0;
 	ctx->wom_field = ctx->cfg.womersley > 0.0 && (ctx->cfg.gravity_x != 0.0 || ctx->cfg.gravity_y != 0.0);
-	bool uniform = true, zero = true;
-	if (force_xy) {
-		const double fx0 = force_xy[0], fy0 = force_xy[1];
-		for (int64_t k = 0; k < n && uniform; k++)
-			if (force_xy[2 * k] != fx0 || force_xy[2 * k + 1] != fy0) uniform = false;
-		zero = uniform && fx0 == 0.0 && fy0 == 0.0;
-		if (uniform) { ctx->fxy_uniform[0] = fx0; ctx->fxy_uniform[1] = fy0; }
-	}
-	if (ctx->wom_field || !uniform) {
-		ctx->fxy_mode = FXY_FIELD;
-		if (!ctx->fxyf) LIFE_CUDA(ctx, cudaMalloc(&ctx->fxyf, sizeof(double) * 2 * L.S));
-		LIFE_CUDA(ctx, cudaMemsetAsync(ctx->fxyf, 0, sizeof(double) * 2 * L.S, ctx->stream));
-		if (force_xy && (rc = upload_field(ctx, force_xy, ctx->fxyf, 2, 0.0))) return rc;
-	} else if (!zero || ctx->cfg.womersley > 0.0) {
-		ctx->fxy_mode = FXY_UNIFORM;
-	}
-
-	// force_ibm of the previous step (restart)
 	ctx->fibm_any = false;
 	ctx->fibm_sites_dirty = false;
 	ctx->fibm_full_dirty = false;
-	if (force_ibm) {
-		bool any = false;
-		for (int64_t k = 0; k < 2 * n && !any; k++) any = force_ibm[k] != 0.0;
-		if (any) {
-			if ((rc = ensure_fibm(ctx))) return rc;
-			if ((rc = upload_field(ctx, force_ibm, ctx->fibm, 2, 0.0))) return rc;
-			ctx->fibm_any = true;
-			ctx->fibm_full_dirty = true;
-		}
+	if (ctx->fibm) LIFE_CUDA(ctx, cudaMemsetAsync(ctx->fibm, 0, sizeof(double) * 2 * L.S, ctx->stream));
+	if (ctx->wom_field) {   // force_xy is a field the sweep recomputes every step (src/Grid.cpp:55-61)
+		if (!ctx->fxyf) LIFE_CUDA(ctx, cudaMalloc(&ctx->fxyf, sizeof(double) * 2 * L.S));
+		LIFE_CUDA(ctx, cudaMemsetAsync(ctx->fxyf, 0, sizeof(double) * 2 * L.S, ctx->stream));
 	}
-	if (!ctx->fibm_any && ctx->fibm) LIFE_CUDA(ctx, cudaMemsetAsync(ctx->fibm, 0, sizeof(double) * 2 * L.S, ctx->stream));
-
 	if (u_in) LIFE_CUDA(ctx, cudaMemcpyAsync(ctx->u_in, u_in, sizeof(double) * 2 * L.Ny, cudaMemcpyHostToDevice, ctx->stream));
 	else LIFE_CUDA(ctx, cudaMemsetAsync(ctx->u_in, 0, sizeof(double) * 2 * L.Ny, ctx->stream));
 	if (rho_in) {
@@ -265,40 +233,146 @@ int life_upload_state(life_ctx *ctx, const double *f, const double *rho, const d
 	} else {
 		std::vector<double> ones((size_t)L.Ny, 1.0);
 		LIFE_CUDA(ctx, cudaMemcpyAsync(ctx->rho_in, ones.data(), sizeof(double) * L.Ny, cudaMemcpyHostToDevice, ctx->stream));
-		LIFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	}
 	// the host arrays belong to the caller: do not return before the copies out of them have completed
 	LIFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-	ctx->have_state = true;
 	return LIFE_OK;
+}
+
+int life_upload_columns(life_ctx *ctx, int64_t il0, int64_t ncols, const double *f, const double *rho, const double *u,
+                        const double *force_xy, const double *force_ibm) {
+	if (!ctx) return LIFE_E_ARG;
+	if (!ctx->uploading) return fail(ctx, LIFE_E_STATE, "life_upload_columns: call life_upload_begin first");
+	const Layout &L = ctx->L;
+	if (il0 < 0 || ncols < 0 || il0 + ncols > L.nxl) return fail(ctx, LIFE_E_ARG, "life_upload_columns: column range outside the slab");
+	if (ncols == 0) return LIFE_OK;
+	if (!f) return fail(ctx, LIFE_E_ARG, "life_upload_columns: f is required");
+	if ((rho == nullptr) != (u == nullptr)) return fail(ctx, LIFE_E_ARG, "life_upload_columns: give both rho and u, or neither");
+	const int has_macro = rho ? 1 : 0;
+	if (ctx->up_macro >= 0 && ctx->up_macro != has_macro)
+		return fail(ctx, LIFE_E_ARG, "life_upload_columns: rho/u must be given for every column range or for none");
+	ctx->up_macro = has_macro;
+	LIFE_CUDA(ctx, cudaSetDevice(ctx->device));
+	const int64_t n = ncols * L.Ny;
+	int rc;
+	if ((rc = upload_field(ctx, f, ctx->fA, 9, il0, ncols))) return rc;
+	if (rho) {
+		if ((rc = ensure_macro(ctx))) return rc;
+		if ((rc = upload_field(ctx, rho, ctx->macro, 1, il0, ncols))) return rc;
+		if ((rc = upload_field(ctx, u, ctx->macro + L.S, 2, il0, ncols))) return rc;
+	}
+
+	// force_xy: none / uniform / field (src/Grid.cpp:1035-1045 makes it uniform; Womersley with gravity makes it a field).
+	// It is kept as two scalars for as long as every node seen so far holds the same pair.
+	double fx0 = ctx->up_fxy0[0], fy0 = ctx->up_fxy0[1];
+	bool chunk_uniform = true;
+	if (force_xy) {
+		if (!ctx->up_fxy_seen) { fx0 = force_xy[0]; fy0 = force_xy[1]; }
+		for (int64_t k = 0; k < n && chunk_uniform; k++)
+			if (force_xy[2 * k] != fx0 || force_xy[2 * k + 1] != fy0) chunk_uniform = false;
+	} else if (ctx->up_fxy_seen && (fx0 != 0.0 || fy0 != 0.0)) {
+		chunk_uniform = false;   // this range is all zero, earlier ones were not
+	}
+	const bool was_uniform = ctx->up_fxy_uniform && !ctx->wom_field;
+	if (was_uniform && chunk_uniform) {
+		if (!ctx->up_fxy_seen) { ctx->up_fxy0[0] = force_xy ? fx0 : 0.0; ctx->up_fxy0[1] = force_xy ? fy0 : 0.0; ctx->up_fxy_seen = true; }
+		ctx->up_ranges.emplace_back(il0, ncols);
+	} else {
+		if (!ctx->fxyf) {
+			LIFE_CUDA(ctx, cudaMalloc(&ctx->fxyf, sizeof(double) * 2 * L.S));
+			LIFE_CUDA(ctx, cudaMemsetAsync(ctx->fxyf, 0, sizeof(double) * 2 * L.S, ctx->stream));
+		}
+		if (was_uniform) {   // first non-uniform range: materialise what was held as scalars
+			for (auto &r : ctx->up_ranges)
+				if ((rc = fill_field(ctx, ctx->fxyf, 2, r.first, r.second, ctx->up_fxy0[0], ctx->up_fxy0[1]))) return rc;
+			ctx->up_ranges.clear();
+		}
+		ctx->up_fxy_uniform = false;
+		ctx->up_fxy_seen = true;
+		if (force_xy) { if ((rc = upload_field(ctx, force_xy, ctx->fxyf, 2, il0, ncols))) return rc; }
+		else if ((rc = fill_field(ctx, ctx->fxyf, 2, il0, ncols, 0.0, 0.0))) return rc;
+	}
+
+	// force_ibm of the previous step (restart)
+	if (force_ibm) {
+		bool any = false;
+		for (int64_t k = 0; k < 2 * n && !any; k++) any = force_ibm[k] != 0.0;
+		if (any) {
+			if ((rc = ensure_fibm(ctx))) return rc;
+			if ((rc = upload_field(ctx, force_ibm, ctx->fibm, 2, il0, ncols))) return rc;
+			ctx->fibm_any = true;
+			ctx->fibm_full_dirty = true;
+		}
+	}
+	// the host arrays belong to the caller: do not return before the copies out of them have completed
+	LIFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	ctx->up_cols += ncols;
+	return LIFE_OK;
+}
+
+int life_upload_end(life_ctx *ctx) {
+	if (!ctx) return LIFE_E_ARG;
+	if (!ctx->uploading) return fail(ctx, LIFE_E_STATE, "life_upload_end: no upload in progress");
+	if (ctx->up_cols != ctx->L.nxl)
+		return fail(ctx, LIFE_E_STATE, "life_upload_end: " + std::to_string(ctx->up_cols) + " of " + std::to_string(ctx->L.nxl) + " columns were uploaded");
+	ctx->stored_macro_valid = ctx->up_macro == 1;
+	if (ctx->wom_field || !ctx->up_fxy_uniform) {
+		ctx->fxy_mode = FXY_FIELD;
+	} else {
+		ctx->fxy_uniform[0] = ctx->up_fxy0[0];
+		ctx->fxy_uniform[1] = ctx->up_fxy0[1];
+		const bool zero = ctx->up_fxy0[0] == 0.0 && ctx->up_fxy0[1] == 0.0;
+		ctx->fxy_mode = (!zero || ctx->cfg.womersley > 0.0) ? FXY_UNIFORM : FXY_NONE;
+	}
+	ctx->up_ranges.clear();
+	ctx->uploading = false;
+	ctx->have_state = true;
+	return life_sync(ctx);
+}
+
+int life_upload_state(life_ctx *ctx, const double *f, const double *rho, const double *u, const double *force_xy,
+                      const double *force_ibm, const double *u_in, const double *rho_in) {
+	if (!ctx) return LIFE_E_ARG;
+	if (!f) return fail(ctx, LIFE_E_ARG, "life_upload_state: f is required");
+	if ((rho == nullptr) != (u == nullptr)) return fail(ctx, LIFE_E_ARG, "life_upload_state: give both rho and u, or neither");
+	int rc;
+	if ((rc = life_upload_begin(ctx, u_in, rho_in))) return rc;
+	if ((rc = life_upload_columns(ctx, 0, ctx->L.nxl, f, rho, u, force_xy, force_ibm))) return rc;
+	return life_upload_end(ctx);
+}
+
+int life_download_columns(life_ctx *ctx, int64_t il0, int64_t ncols, double *f, double *rho, double *u, double *force_ibm) {
+	if (!ctx) return LIFE_E_ARG;
+	if (!ctx->have_state) return fail(ctx, LIFE_E_STATE, "life_download_columns: no state uploaded");
+	const Layout &L = ctx->L;
+	if (il0 < 0 || ncols < 0 || il0 + ncols > L.nxl) return fail(ctx, LIFE_E_ARG, "life_download_columns: column range outside the slab");
+	if (ncols == 0) return LIFE_OK;
+	LIFE_CUDA(ctx, cudaSetDevice(ctx->device));
+	int rc;
+	if (f && (rc = download_field(ctx, f, ctx->fA, 9, il0, ncols))) return rc;
+	if (rho || u) {
+		if (!ctx->stored_macro_valid) {   // otherwise `macro` already holds exactly what the host uploaded
+			if ((rc = ensure_macro(ctx))) return rc;
+			if ((rc = launch_macro(ctx, ctx->macro, il0, ncols))) return rc;
+		}
+		if (rho && (rc = download_field(ctx, rho, ctx->macro, 1, il0, ncols))) return rc;
+		if (u && (rc = download_field(ctx, u, ctx->macro + L.S, 2, il0, ncols))) return rc;
+	}
+	if (force_ibm) {
+		if (ctx->fibm) { if ((rc = download_field(ctx, force_ibm, ctx->fibm, 2, il0, ncols))) return rc; }
+		else memset(force_ibm, 0, sizeof(double) * 2 * (size_t)(ncols * L.Ny));
+	}
+	return life_sync(ctx);
 }
 
 int life_download_macro(life_ctx *ctx, double *rho, double *u) {
 	if (!ctx) return LIFE_E_ARG;
-	if (!ctx->have_state) return fail(ctx, LIFE_E_STATE, "life_download_macro: no state uploaded");
-	LIFE_CUDA(ctx, cudaSetDevice(ctx->device));
-	int rc;
-	if (!ctx->stored_macro_valid) {   // otherwise `macro` already holds exactly what the host uploaded
-		if ((rc = ensure_macro(ctx))) return rc;
-		if ((rc = launch_macro(ctx, ctx->macro))) return rc;
-	}
-	if (rho && (rc = download_field(ctx, rho, ctx->macro, 1))) return rc;
-	if (u && (rc = download_field(ctx, u, ctx->macro + ctx->L.S, 2))) return rc;
-	return life_sync(ctx);
+	return life_download_columns(ctx, 0, ctx->L.nxl, nullptr, rho, u, nullptr);
 }
 
 int life_download_state(life_ctx *ctx, double *f, double *rho, double *u, double *force_ibm) {
 	if (!ctx) return LIFE_E_ARG;
-	if (!ctx->have_state) return fail(ctx, LIFE_E_STATE, "life_download_state: no state uploaded");
-	LIFE_CUDA(ctx, cudaSetDevice(ctx->device));
-	int rc;
-	if (f && (rc = download_field(ctx, f, ctx->fA, 9))) return rc;
-	if ((rho || u) && (rc = life_download_macro(ctx, rho, u))) return rc;
-	if (force_ibm) {
-		if (ctx->fibm) { if ((rc = download_field(ctx, force_ibm, ctx->fibm, 2))) return rc; }
-		else memset(force_ibm, 0, sizeof(double) * 2 * (size_t)(ctx->L.nxl * ctx->L.Ny));
-	}
-	return life_sync(ctx);
+	return life_download_columns(ctx, 0, ctx->L.nxl, f, rho, u, force_ibm);
 }
 
 int life_max_speed(life_ctx *ctx, double *vmax, int32_t *has_nan, int64_t *nan_i, int64_t *nan_j) {

@@ -91,6 +91,13 @@ struct life_ctx {
 	double fxy_uniform[2] = {0, 0};       // current uniform force_xy (what GridClass::force_xy holds right now)
 	bool wom_field = false;               // Womersley with gravity: force_xy is a field recomputed every step
 	bool have_state = false;
+	// streaming upload in progress (life_upload_begin .. life_upload_end)
+	bool uploading = false;
+	int up_macro = -1;                    // -1 undecided, 0 rho/u derived from f, 1 rho/u uploaded
+	int64_t up_cols = 0;                  // columns received so far
+	bool up_fxy_seen = false, up_fxy_uniform = true;
+	double up_fxy0[2] = {0, 0};
+	std::vector<std::pair<int64_t, int64_t>> up_ranges;   // column ranges received while force_xy was still uniform
 	bool stored_macro_valid = false;      // `macro` holds uploaded rho_n/u_n to be used by the next step
 	bool fibm_any = false;                // force_ibm may be non-zero somewhere
 	bool fibm_sites_dirty = false;        // non-zero only at the current support sites
@@ -139,9 +146,10 @@ int launch_boundary(life_ctx *ctx, const StepScalars &sc);
 // halo.cu
 int exchange_x(life_ctx *ctx);
 // lbm_io.cu
-int upload_field(life_ctx *ctx, const double *h, double *planes, int ncomp, double fill_missing);
-int download_field(life_ctx *ctx, double *h, const double *planes, int ncomp);
-int launch_macro(life_ctx *ctx, double *out_planes);
+int upload_field(life_ctx *ctx, const double *h, double *planes, int ncomp, int64_t il0, int64_t ncols);
+int download_field(life_ctx *ctx, double *h, const double *planes, int ncomp, int64_t il0, int64_t ncols);
+int fill_field(life_ctx *ctx, double *planes, int ncomp, int64_t il0, int64_t ncols, double v0, double v1);
+int launch_macro(life_ctx *ctx, double *out_planes, int64_t il0, int64_t ncols);
 int launch_max_speed(life_ctx *ctx, double *vmax, int32_t *has_nan, int64_t *nan_id);
 int ensure_scratch(life_ctx *ctx, size_t bytes);
 int ensure_macro(life_ctx *ctx);

@@ -103,8 +103,26 @@ __global__ void __launch_bounds__(256) k_bulk_direct(const BulkArgs a) {
 // Population with cy = +1: row q goes to row q+1.  The aligned pair (R+2l, R+2l+1) of the destination therefore consists of
 // the upper element of lane l-1 and the lower element of lane l: one shuffle-up, then lanes 1..31 issue one aligned 16-byte
 // store each; lane 0 stores row R+1 alone and lane 31 stores row R+64 alone.  cy = -1 is the mirror image (shuffle-down).
-template <int COLL, int MODE>
-__global__ void __launch_bounds__(256) k_bulk_shuffle(const BulkArgs a) {
+// HINT selects the cache policy of the population traffic: 0 = read-only path loads + default stores, 1 = streaming
+// (evict-first) loads and stores.  BLOCK is the CTA size.  Both only matter for tuning (cfg.tune); results are identical.
+template <int HINT>
+__device__ __forceinline__ double2 ld_pair(const double *p) {
+	if (HINT == 1) return __ldcs(reinterpret_cast<const double2 *>(p));
+	return __ldg(reinterpret_cast<const double2 *>(p));
+}
+template <int HINT>
+__device__ __forceinline__ void st_pair(double *p, double x, double y) {
+	if (HINT == 1) __stcs(reinterpret_cast<double2 *>(p), make_double2(x, y));
+	else *reinterpret_cast<double2 *>(p) = make_double2(x, y);
+}
+template <int HINT>
+__device__ __forceinline__ void st_one(double *p, double x) {
+	if (HINT == 1) __stcs(p, x);
+	else *p = x;
+}
+
+template <int COLL, int MODE, int BLOCK = 256, int HINT = 0>
+__global__ void __launch_bounds__(BLOCK) k_bulk_shuffle(const BulkArgs a) {
 	const int64_t col = a.c_first + blockIdx.x / a.tiles;
 	const int64_t j = ((int64_t)(blockIdx.x % a.tiles) * blockDim.x + threadIdx.x) * 2;
 	const int lane = threadIdx.x & 31;
@@ -117,7 +135,7 @@ __global__ void __launch_bounds__(256) k_bulk_shuffle(const BulkArgs a) {
 #pragma unroll
 	for (int v = 0; v < NV; v++) {
 		// rows beyond Ny still lie inside the padded pitch (ghost row + padding), so the vector load is always in bounds
-		const double2 t = __ldg(reinterpret_cast<const double2 *>(a.fin + v * a.L.S + idx));
+		const double2 t = ld_pair<HINT>(a.fin + v * a.L.S + idx);
 		f0[v] = t.x; f1[v] = t.y;
 	}
 	if (v0ok) node_update<COLL, MODE>(a, idx, f0, o0);
@@ -126,22 +144,22 @@ __global__ void __launch_bounds__(256) k_bulk_shuffle(const BulkArgs a) {
 	for (int v = 0; v < NV; v++) {
 		double *dst = a.fout + v * a.L.S + idx + LIFE_CX(v) * a.L.P;
 		if (LIFE_CY(v) == 0) {
-			if (v1ok) *reinterpret_cast<double2 *>(dst) = make_double2(o0[v], o1[v]);
-			else if (v0ok) dst[0] = o0[v];
+			if (v1ok) st_pair<HINT>(dst, o0[v], o1[v]);
+			else if (v0ok) st_one<HINT>(dst, o0[v]);
 		} else if (LIFE_CY(v) == 1) {
 			// destination rows j+1, j+2.  aligned pair (j, j+1) = { upper of lane-1 , own lower }
 			const double up = __shfl_up_sync(0xffffffffu, o1[v], 1);
-			if (lane == 0) { if (v0ok) dst[1] = o0[v]; }
-			else if (v0ok) *reinterpret_cast<double2 *>(dst) = make_double2(up, o0[v]);
-			else if (j - 1 < a.L.Ny) dst[0] = up;            // first thread past the end still owns row j (= upper of lane-1)
-			if (lane == 31 && v1ok) dst[2] = o1[v];
+			if (lane == 0) { if (v0ok) st_one<HINT>(dst + 1, o0[v]); }
+			else if (v0ok) st_pair<HINT>(dst, up, o0[v]);
+			else if (j - 1 < a.L.Ny) st_one<HINT>(dst, up);            // first thread past the end still owns row j (= upper of lane-1)
+			if (lane == 31 && v1ok) st_one<HINT>(dst + 2, o1[v]);
 		} else {
 			// destination rows j-1, j.  aligned pair (j, j+1) = { own upper , lower of lane+1 }
 			const double dn = __shfl_down_sync(0xffffffffu, o0[v], 1);
-			if (lane == 0 && v0ok) dst[-1] = o0[v];
-			if (lane == 31) { if (v1ok) dst[0] = o1[v]; }
-			else if (j + 2 < a.L.Ny) { *reinterpret_cast<double2 *>(dst) = make_double2(o1[v], dn); }
-			else if (v1ok) dst[0] = o1[v];
+			if (lane == 0 && v0ok) st_one<HINT>(dst - 1, o0[v]);
+			if (lane == 31) { if (v1ok) st_one<HINT>(dst, o1[v]); }
+			else if (j + 2 < a.L.Ny) st_pair<HINT>(dst, o1[v], dn);
+			else if (v1ok) st_one<HINT>(dst, o1[v]);
 		}
 	}
 }
@@ -149,15 +167,23 @@ __global__ void __launch_bounds__(256) k_bulk_shuffle(const BulkArgs a) {
 template <int COLL, int MODE>
 static int launch_one(life_ctx *ctx, const BulkArgs &a0, int64_t c_count, cudaStream_t st) {
 	BulkArgs a = a0;
-	const int threads = 256;
 	const bool staged = ctx->cfg.kernel != LIFE_KERNEL_DIRECT;   // AUTO → SHUFFLE
+	// cfg.tune (measurement only, force-free shuffle kernel): tens digit = cache hint, units digit = CTA size 1:128 2:256 3:512
+	const int tune = (staged && MODE == M_NONE) ? ctx->cfg.tune : 0;
+	const int threads = (tune % 10 == 1) ? 128 : ((tune % 10 == 3) ? 512 : 256);
 	const int64_t rows_per_block = staged ? 2 * threads : threads;
 	a.tiles = (a.L.Ny + rows_per_block - 1) / rows_per_block;
 	const int64_t blocks = a.tiles * c_count;
 	if (blocks <= 0) return LIFE_OK;
 	if (blocks > 0x7fffffffLL) return fail(ctx, LIFE_E_ARG, "bulk sweep: grid too large");
-	if (staged) k_bulk_shuffle<COLL, MODE><<<(unsigned)blocks, threads, 0, st>>>(a);
-	else k_bulk_direct<COLL, MODE><<<(unsigned)blocks, threads, 0, st>>>(a);
+	if (!staged) k_bulk_direct<COLL, MODE><<<(unsigned)blocks, threads, 0, st>>>(a);
+	else if (MODE != M_NONE || tune == 0 || tune == 2) k_bulk_shuffle<COLL, MODE><<<(unsigned)blocks, threads, 0, st>>>(a);
+	else if (tune == 1) k_bulk_shuffle<COLL, M_NONE, 128, 0><<<(unsigned)blocks, threads, 0, st>>>(a);
+	else if (tune == 3) k_bulk_shuffle<COLL, M_NONE, 512, 0><<<(unsigned)blocks, threads, 0, st>>>(a);
+	else if (tune == 11) k_bulk_shuffle<COLL, M_NONE, 128, 1><<<(unsigned)blocks, threads, 0, st>>>(a);
+	else if (tune == 12) k_bulk_shuffle<COLL, M_NONE, 256, 1><<<(unsigned)blocks, threads, 0, st>>>(a);
+	else if (tune == 13) k_bulk_shuffle<COLL, M_NONE, 512, 1><<<(unsigned)blocks, threads, 0, st>>>(a);
+	else return fail(ctx, LIFE_E_ARG, "bulk sweep: unknown cfg.tune");
 	ctx->launches++;
 	LIFE_CUDA(ctx, cudaGetLastError());
 	return LIFE_OK;

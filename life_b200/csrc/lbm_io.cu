@@ -64,38 +64,57 @@ static int64_t chunk_columns(life_ctx *ctx, int ncomp) {
 	return cols;
 }
 
-int upload_field(life_ctx *ctx, const double *h, double *planes, int ncomp, double) {
+// host chunk `h` = columns [il0, il0 + ncols) of a reference-layout array with `ncomp` doubles per node
+int upload_field(life_ctx *ctx, const double *h, double *planes, int ncomp, int64_t il0, int64_t ncols) {
 	const Layout &L = ctx->L;
 	const int64_t cols = chunk_columns(ctx, ncomp);
 	int rc = ensure_scratch(ctx, sizeof(double) * (size_t)(cols * L.Ny * ncomp));
 	if (rc) return rc;
-	for (int64_t il0 = 0; il0 < L.nxl; il0 += cols) {
-		const int64_t nc = (il0 + cols <= L.nxl) ? cols : L.nxl - il0;
+	for (int64_t c0 = 0; c0 < ncols; c0 += cols) {
+		const int64_t nc = (c0 + cols <= ncols) ? cols : ncols - c0;
 		const int64_t n_elems = nc * L.Ny * ncomp;
-		LIFE_CUDA(ctx, cudaMemcpyAsync(ctx->scratch, h + il0 * L.Ny * ncomp, sizeof(double) * n_elems,
+		LIFE_CUDA(ctx, cudaMemcpyAsync(ctx->scratch, h + c0 * L.Ny * ncomp, sizeof(double) * n_elems,
 		                               cudaMemcpyHostToDevice, ctx->stream));
-		k_unpack<<<(unsigned)((n_elems + 255) / 256), 256, 0, ctx->stream>>>(ctx->scratch, planes, L, ncomp, il0, n_elems);
+		k_unpack<<<(unsigned)((n_elems + 255) / 256), 256, 0, ctx->stream>>>(ctx->scratch, planes, L, ncomp, il0 + c0, n_elems);
 		ctx->launches++;
 		LIFE_CUDA(ctx, cudaGetLastError());
 	}
 	return LIFE_OK;
 }
 
-int download_field(life_ctx *ctx, double *h, const double *planes, int ncomp) {
+int download_field(life_ctx *ctx, double *h, const double *planes, int ncomp, int64_t il0, int64_t ncols) {
 	const Layout &L = ctx->L;
 	const int64_t cols = chunk_columns(ctx, ncomp);
 	int rc = ensure_scratch(ctx, sizeof(double) * (size_t)(cols * L.Ny * ncomp));
 	if (rc) return rc;
-	for (int64_t il0 = 0; il0 < L.nxl; il0 += cols) {
-		const int64_t nc = (il0 + cols <= L.nxl) ? cols : L.nxl - il0;
+	for (int64_t c0 = 0; c0 < ncols; c0 += cols) {
+		const int64_t nc = (c0 + cols <= ncols) ? cols : ncols - c0;
 		const int64_t n_elems = nc * L.Ny * ncomp;
-		k_pack<<<(unsigned)((n_elems + 255) / 256), 256, 0, ctx->stream>>>(ctx->scratch, planes, L, ncomp, il0, n_elems);
+		k_pack<<<(unsigned)((n_elems + 255) / 256), 256, 0, ctx->stream>>>(ctx->scratch, planes, L, ncomp, il0 + c0, n_elems);
 		ctx->launches++;
 		LIFE_CUDA(ctx, cudaGetLastError());
-		LIFE_CUDA(ctx, cudaMemcpyAsync(h + il0 * L.Ny * ncomp, ctx->scratch, sizeof(double) * n_elems,
+		LIFE_CUDA(ctx, cudaMemcpyAsync(h + c0 * L.Ny * ncomp, ctx->scratch, sizeof(double) * n_elems,
 		                               cudaMemcpyDeviceToHost, ctx->stream));
 	}
 	LIFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return LIFE_OK;
+}
+
+// planes[k] := vals[k] on columns [il0, il0 + ncols)
+__global__ void k_fill(double *__restrict__ planes, Layout L, int ncomp, int64_t il0, int64_t n_nodes, double v0, double v1) {
+	const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= n_nodes) return;
+	const int64_t idx = L.node(il0 + e / L.Ny, e % L.Ny);
+	planes[idx] = v0;
+	if (ncomp > 1) planes[L.S + idx] = v1;
+}
+
+int fill_field(life_ctx *ctx, double *planes, int ncomp, int64_t il0, int64_t ncols, double v0, double v1) {
+	const int64_t n = ncols * ctx->L.Ny;
+	if (n <= 0) return LIFE_OK;
+	k_fill<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(planes, ctx->L, ncomp, il0, n, v0, v1);
+	ctx->launches++;
+	LIFE_CUDA(ctx, cudaGetLastError());
 	return LIFE_OK;
 }
 
@@ -125,9 +144,9 @@ __device__ __forceinline__ void node_macro(const MacroArgs &a, int64_t idx, doub
 	}
 }
 
-__global__ void __launch_bounds__(256) k_macro(const MacroArgs a, double *out) {
+__global__ void __launch_bounds__(256) k_macro(const MacroArgs a, double *out, int64_t c_first) {
 	const int64_t tiles = (a.L.Ny + blockDim.x - 1) / blockDim.x;
-	const int64_t col = 1 + blockIdx.x / tiles;
+	const int64_t col = c_first + blockIdx.x / tiles;
 	const int64_t j = (int64_t)(blockIdx.x % tiles) * blockDim.x + threadIdx.x;
 	if (j >= a.L.Ny) return;
 	const int64_t idx = col * a.L.P + j + JOFF;
@@ -149,11 +168,12 @@ static MacroArgs macro_args(life_ctx *ctx) {
 	return a;
 }
 
-int launch_macro(life_ctx *ctx, double *out_planes) {
+int launch_macro(life_ctx *ctx, double *out_planes, int64_t il0, int64_t ncols) {
 	MacroArgs a = macro_args(ctx);
 	const int64_t tiles = (a.L.Ny + 255) / 256;
-	const int64_t blocks = tiles * a.L.nxl;
-	k_macro<<<(unsigned)blocks, 256, 0, ctx->stream>>>(a, out_planes);
+	const int64_t blocks = tiles * ncols;
+	if (blocks <= 0) return LIFE_OK;
+	k_macro<<<(unsigned)blocks, 256, 0, ctx->stream>>>(a, out_planes, il0 + 1);
 	ctx->launches++;
 	LIFE_CUDA(ctx, cudaGetLastError());
 	return LIFE_OK;

@@ -171,3 +171,125 @@ def test_large_lattice_properties():
     assert np.abs(v).max() > 0.05
     ctx.close()
     ctx2.close()
+
+
+def test_streaming_upload_and_download_equal_the_whole_slab_calls():
+    """life_upload_begin/columns/end and life_download_columns (host image streamed in column ranges, e.g. from a restart file)
+    are the same operation as life_upload_state / life_download_state: identical trajectory, bit for bit."""
+    from life_b200 import capi
+    g = K.golden("t_womersley")       # periodic x, uniform force_xy that changes every step
+    o = K.make_oracle(g)
+    a = capi.Context(K.life_config(o.params, o))
+    K.upload_from_oracle(a, o)
+    b = capi.Context(K.life_config(o.params, o))
+    f, rho, u, fxy, fibm = (o.get(n) for n in ("f", "rho", "u", "force_xy", "force_ibm"))
+    b.upload_begin(o.get("u_in"), o.get("rho_in"))
+    Nx = o.Nx
+    cuts = [(17, Nx - 17), (0, 5), (5, 12)]          # out of order, uneven
+    for il0, nc in cuts:
+        b.upload_columns(il0, nc, f[il0:il0 + nc], rho[il0:il0 + nc], u[il0:il0 + nc], fxy[il0:il0 + nc], fibm[il0:il0 + nc])
+    b.upload_end()
+    for t in range(1, 31):
+        a.step(t)
+        b.step(t)
+    sa = a.download_state()
+    for il0, nc in cuts:
+        pf, pr, pu, pi = np.empty((nc, o.Ny, 9)), np.empty((nc, o.Ny)), np.empty((nc, o.Ny, 2)), np.empty((nc, o.Ny, 2))
+        b.download_columns_into(il0, nc, pf, pr, pu, pi)
+        assert np.array_equal(pf, sa["f"][il0:il0 + nc])
+        assert np.array_equal(pr, sa["rho"][il0:il0 + nc])
+        assert np.array_equal(pu, sa["u"][il0:il0 + nc])
+        assert np.array_equal(pi, sa["force_ibm"][il0:il0 + nc])
+    a.close()
+    b.close()
+
+
+def test_streaming_upload_with_a_force_field_discovered_late():
+    """force_xy uniform in the first ranges and different in a later one: the scalars held so far are materialised into the
+    field planes; the result equals the whole-slab upload of the same non-uniform force."""
+    from life_b200 import capi
+    g = K.golden("t_periodic_bgk")
+    o = K.make_oracle(g)
+    Nx, Ny = o.Nx, o.Ny
+    fxy = np.zeros((Nx, Ny, 2))
+    fxy[..., 0] = 1e-5
+    fxy[30:, :, 1] = 2e-5 * np.cos(np.arange(Ny) * 0.2)[None, :]
+    f, rho, u = o.get("f"), o.get("rho"), o.get("u")
+    a = capi.Context(K.life_config(o.params, o))
+    a.upload_state(f, rho, u, fxy, None, o.get("u_in"), o.get("rho_in"))
+    b = capi.Context(K.life_config(o.params, o))
+    b.upload_begin(o.get("u_in"), o.get("rho_in"))
+    for il0, nc in [(0, 10), (10, 15), (25, Nx - 25)]:
+        b.upload_columns(il0, nc, f[il0:il0 + nc], rho[il0:il0 + nc], u[il0:il0 + nc], fxy[il0:il0 + nc], None)
+    b.upload_end()
+    o.set("force_xy", fxy)
+    for t in range(1, 21):
+        a.step(t)
+        b.step(t)
+    o.step(20)
+    sa, sb = a.download_state(), b.download_state()
+    for name in ("f", "rho", "u"):
+        assert np.array_equal(sa[name], sb[name]), name
+        assert K.rel_l2(sb[name], o.get(name)) < K.TOL, name
+    a.close()
+    b.close()
+
+
+def test_upload_protocol_errors():
+    from life_b200 import capi
+    g = K.golden("t_periodic_bgk")
+    o = K.make_oracle(g)
+    c = capi.Context(K.life_config(o.params, o))
+    f = o.get("f")
+    with pytest.raises(capi.LifeError) as e:
+        c.upload_columns(0, 4, f[:4])
+    assert e.value.code == capi.E_STATE
+    c.upload_begin()
+    c.upload_columns(0, 4, f[:4])
+    with pytest.raises(capi.LifeError) as e:
+        c.upload_end()                      # columns missing
+    assert e.value.code == capi.E_STATE
+    with pytest.raises(capi.LifeError) as e:
+        c.step(1)                           # no complete state yet
+    assert e.value.code == capi.E_STATE
+    with pytest.raises(capi.LifeError) as e:
+        c.upload_columns(o.Nx - 2, 4, f[:4])
+    assert e.value.code == capi.E_ARG
+    c.close()
+
+
+def test_conservation_at_full_size():
+    """BASELINE.json's full single-GPU size (16384^2): in a fully periodic box without forces mass and momentum are conserved
+    by the scheme — a size-independent property checked where the oracle cannot go (the reference's int indices overflow at
+    15447^2).  The state is streamed in column ranges so the host never holds the 19 GB image."""
+    from life_b200 import capi
+    from tests.initstate import wavy_state
+    N = 16384
+    cfg = capi.Config(Nx=N, Ny=N, omega=1.7, wall_left=0, wall_right=0, wall_bottom=0, wall_top=0, Dx=1.0, Dt=1.0, Dm=1.0)
+    c = capi.Context(cfg)
+    C = 1024
+    c.upload_begin()
+    mass0 = 0.0
+    mom0 = np.zeros(2)
+    cx = np.array([0, 1, -1, 0, 0, 1, -1, 1, -1.0])
+    cy = np.array([0, 0, 0, 1, -1, 1, -1, -1, 1.0])
+    # a wavy patch of C columns, periodic in both directions on its own, tiled along x
+    f, _, _ = wavy_state(C, N, False)
+    for il0 in range(0, N, C):
+        c.upload_columns(il0, C, f)
+    c.upload_end()
+    mass0 = f.sum() * (N // C)
+    mom0 = np.array([(f * cx).sum(), (f * cy).sum()]) * (N // C)
+    for t in range(1, 41):
+        c.step(t)
+    mass, mom = 0.0, np.zeros(2)
+    buf = np.empty((C, N, 9))
+    for il0 in range(0, N, C):
+        c.download_columns_into(il0, C, buf)
+        mass += buf.sum()
+        mom += np.array([(buf * cx).sum(), (buf * cy).sum()])
+    assert abs(mass - mass0) < 1e-11 * mass0
+    assert np.all(np.abs(mom - mom0) < 1e-9 * np.abs(mom0).max() + 1e-6)
+    vmax, has_nan, _, _ = c.max_speed()
+    assert not has_nan and 0.0 < vmax < 0.2
+    c.close()

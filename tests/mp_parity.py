@@ -87,15 +87,16 @@ def main():
                     ok = False
                     msgs.append("%s %.3e" % (name, err))
         for name in ("rho", "u", "f", "force_ibm"):
-            err = K.rel_l2(st[name], o.get(name)[b:e], floor=1e-12 if name == "force_ibm" else (1e-6 if name == "u" else 0.0))
+            err = K.rel_l2(st[name], o.get(name)[b:e], floor=1e-12 if name == "force_ibm" else (1e-5 if name == "u" else 0.0))
             if not err < K.TOL:
                 ok = False
                 msgs.append("slab %s %.3e" % (name, err))
     else:
         for name in ("rho", "u", "f"):
-            # a slab can lie where the flow has not arrived yet (ChannelFlow's outlet half): u there is rounding noise of
-            # the O(1) populations, so the denominator is floored at 1e-6 per entry (error bar 1e-16 absolute)
-            err = K.rel_l2(st[name], o.get(name)[b:e], floor=1e-6 if name == "u" else 0.0)
+            # a slab can lie where the flow has not arrived yet (ChannelFlow downstream of the inlet front): u = sum(c f)/rho
+            # there is the cancellation noise of O(0.1) populations, ~1e-16 absolute in the reference too, so the
+            # denominator is floored at 1e-5 per entry (error bar 1e-15 absolute)
+            err = K.rel_l2(st[name], o.get(name)[b:e], floor=1e-5 if name == "u" else 0.0)
             if not err < K.TOL:
                 ok = False
                 msgs.append("%s %.3e" % (name, err))

@@ -182,7 +182,8 @@ int life_sync(life_ctx *ctx);
  * and computeEpsilon src/Objects.cpp:235-321): pos, vel [n*2] in physical units, ds, epsilon [n].
  * ALL markers of the simulation on every rank.  The device recomputes every marker's support exactly as
  * IBMNodeClass::findSupport does (src/IBMNode.cpp:139-179, delta of inc/Utils.h:220-232).
- * May be called every sub-iteration.  Returns LIFE_E_SUPPORT if a marker collects more than 9 sites.
+ * May be called every sub-iteration.  Asynchronous (the arrays are copied out before it returns): if a marker collects more
+ * than 9 sites, LIFE_E_SUPPORT is returned by the next synchronising call (life_ibm_interp, life_sync).
  */
 int life_ibm_set_markers(life_ctx *ctx, int64_t n, const double *pos, const double *vel, const double *ds,
                          const double *epsilon);
@@ -197,6 +198,26 @@ int life_ibm_interp(life_ctx *ctx, double *force_out);
  * supports / ds / epsilon of the last life_ibm_set_markers; updateMacroscopic (:97-136) is implicit (rho, u are
  * always evaluated from f and the current forces).  Asynchronous. */
 int life_ibm_spread(life_ctx *ctx);
+
+/*
+ * OPTIONAL (the default integration keeps this on the host with LAPACK):
+ * ObjectsClass::computeEpsilon (src/Objects.cpp:235-321) with Utils::solveLAPACK (src/Utils.cpp:288-311) on the device.
+ * For each of n_bodies groups of markers — group b = members[body_first[b] .. body_first[b+1]), indices into the arrays of the
+ * last life_ibm_set_markers; one group holding every marker reproduces UNI_EPSILON — assemble
+ * A_ij = ds_j * sum_s delta_i(s) delta(x_j/Dx - site_s) over the supports of marker i (bit-exact) and solve A eps = 1 by LU with
+ * partial pivoting (dgetrf/dgetrs('T') semantics; eps agrees with LAPACK to rounding x cond(A)).  Updates the device's epsilon
+ * of the member markers (non-members keep theirs) and returns all n marker epsilons in epsilon_out (may be NULL).  Synchronises.
+ */
+int life_ibm_compute_epsilon(life_ctx *ctx, int64_t n_bodies, const int64_t *body_first, const int64_t *members,
+                             double *epsilon_out);
+
+/*
+ * OPTIONAL, the data-parallel half of the above only: assemble the matrices (bit-exact) and return them, body after body,
+ * A_out[ sum_{b'<b} dim_b'^2 + i*dim_b + j ] = A_ij of body b — exactly the row-major array computeEpsilon hands to
+ * Utils::solveLAPACK (src/Objects.cpp:304-307).  The host keeps its own LAPACK solve, so epsilon is bit-identical to the
+ * reference's while the O(dim^2 * 9) delta evaluations (serial per body on the CPU) run on the GPU.  Synchronises.
+ */
+int life_ibm_assemble_epsilon(life_ctx *ctx, int64_t n_bodies, const int64_t *body_first, const int64_t *members, double *A_out);
 
 /* Overwrite the marker forces kept on the device (restart: src/Objects.cpp:1226-1257 stores them). */
 int life_ibm_set_forces(life_ctx *ctx, const double *force);

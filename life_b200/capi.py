@@ -24,7 +24,7 @@ EXPORTS = [
     "life_slab_range",
     "life_upload_state", "life_upload_begin", "life_upload_columns", "life_upload_end", "life_download_columns",
     "life_download_macro", "life_download_state", "life_max_speed", "life_step", "life_step_n",
-    "life_sync", "life_ibm_set_markers", "life_ibm_interp", "life_ibm_spread", "life_ibm_set_forces",
+    "life_sync", "life_ibm_set_markers", "life_ibm_interp", "life_ibm_spread", "life_ibm_compute_epsilon", "life_ibm_assemble_epsilon", "life_ibm_set_forces",
     "life_ibm_get_interp", "life_ibm_get_supports", "life_get_boundary", "life_get_types", "life_launch_count",
     "life_bulk_kernel_ms", "life_set_profiling",
 ]
@@ -102,6 +102,8 @@ def load():
     L.life_ibm_set_markers.argtypes = [vp, i64, vp, vp, vp, vp]
     L.life_ibm_interp.argtypes = [vp, vp]
     L.life_ibm_spread.argtypes = [vp]
+    L.life_ibm_compute_epsilon.argtypes = [vp, i64, vp, vp, vp]
+    L.life_ibm_assemble_epsilon.argtypes = [vp, i64, vp, vp, vp]
     L.life_ibm_set_forces.argtypes = [vp, vp]
     L.life_ibm_get_interp.argtypes = [vp, vp, vp]
     L.life_ibm_get_supports.argtypes = [vp, vp, vp, vp, vp]
@@ -248,6 +250,28 @@ class Context:
 
     def ibm_spread(self):
         self._ck(self.L.life_ibm_spread(self.h))
+
+    def ibm_compute_epsilon(self, groups):
+        """groups: list of integer index arrays (one per body); returns the epsilon of every marker"""
+        first = np.zeros(len(groups) + 1, np.int64)
+        first[1:] = np.cumsum([len(g) for g in groups])
+        members = np.ascontiguousarray(np.concatenate(groups) if groups else np.zeros(0), np.int64)
+        out = np.empty(self.n_markers)
+        self._ck(self.L.life_ibm_compute_epsilon(self.h, len(groups), _ptr(first), _ptr(members), _ptr(out)))
+        return out
+
+    def ibm_assemble_epsilon(self, groups):
+        """list of dim x dim matrices A (row-major, as handed to solveLAPACK), one per group"""
+        first = np.zeros(len(groups) + 1, np.int64)
+        first[1:] = np.cumsum([len(g) for g in groups])
+        members = np.ascontiguousarray(np.concatenate(groups) if groups else np.zeros(0), np.int64)
+        flat = np.empty(int(sum(len(g) ** 2 for g in groups)))
+        self._ck(self.L.life_ibm_assemble_epsilon(self.h, len(groups), _ptr(first), _ptr(members), _ptr(flat)))
+        out, off = [], 0
+        for g in groups:
+            out.append(flat[off:off + len(g) ** 2].reshape(len(g), len(g)).copy())
+            off += len(g) ** 2
+        return out
 
     def ibm_set_forces(self, force):
         force = _f64(force)

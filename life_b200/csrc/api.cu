@@ -51,7 +51,7 @@ static void free_ctx(life_ctx *ctx) {
 	if (ctx->comm) ncclCommDestroy(ctx->comm);
 	cudaFree(ctx->fA); cudaFree(ctx->fB); cudaFree(ctx->macro); cudaFree(ctx->fibm); cudaFree(ctx->fxyf);
 	cudaFree(ctx->cell_head); cudaFree(ctx->u_in); cudaFree(ctx->rho_in); cudaFree(ctx->delU); cudaFree(ctx->bc);
-	cudaFree(ctx->scratch); cudaFree(ctx->d_red);
+	cudaFree(ctx->scratch); cudaFree(ctx->d_red); cudaFree(ctx->eps_buf);
 	if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
 	for (auto &p : ctx->prof_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
 	if (ctx->ev_edge) cudaEventDestroy(ctx->ev_edge);
@@ -462,6 +462,7 @@ int life_sync(life_ctx *ctx) {
 		LIFE_NCCL(ctx, ncclCommGetAsyncError(ctx->comm, &ar));
 		if (ar != ncclSuccess) return fail(ctx, LIFE_E_NCCL, std::string("asynchronous NCCL error: ") + ncclGetErrorString(ar));
 	}
+	if (ctx->mk.n > 0) return ibm_check(ctx);   // marker errors latched on the device since the last check
 	return LIFE_OK;
 }
 
@@ -530,6 +531,18 @@ int life_ibm_spread(life_ctx *ctx) {
 	if (!ctx->have_state) return fail(ctx, LIFE_E_STATE, "life_ibm_spread: no state uploaded");
 	LIFE_CUDA(ctx, cudaSetDevice(ctx->device));
 	return ibm_spread(ctx);
+}
+
+int life_ibm_compute_epsilon(life_ctx *ctx, int64_t n_bodies, const int64_t *body_first, const int64_t *members, double *epsilon_out) {
+	if (!ctx) return LIFE_E_ARG;
+	LIFE_CUDA(ctx, cudaSetDevice(ctx->device));
+	return ibm_compute_epsilon(ctx, n_bodies, body_first, members, epsilon_out);
+}
+
+int life_ibm_assemble_epsilon(life_ctx *ctx, int64_t n_bodies, const int64_t *body_first, const int64_t *members, double *A_out) {
+	if (!ctx) return LIFE_E_ARG;
+	LIFE_CUDA(ctx, cudaSetDevice(ctx->device));
+	return ibm_assemble_epsilon(ctx, n_bodies, body_first, members, A_out);
 }
 
 int life_ibm_set_forces(life_ctx *ctx, const double *force) {

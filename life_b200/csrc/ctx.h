@@ -1,7 +1,7 @@
 // Context, device layout and internal kernel-launcher declarations of liblife_b200.
 #pragma once
 #include <cuda_runtime.h>
-#include <nccl.h>
+#include "nccl_dyn.h"
 #include <cstdint>
 #include <string>
 #include <vector>
@@ -53,14 +53,17 @@ struct StepScalars {      // per-step host-computed scalars
 
 struct MarkerBuffers {
 	int64_t n = 0, cap = 0;
-	double *pos = nullptr, *vel = nullptr, *ds = nullptr, *eps = nullptr;   // device, SoA: pos[2n] = x0 y0 x1 y1 ...
+	double *in = nullptr;             // device: pos[2n] | vel[2n] | ds[n] | eps[n] in one array (one copy per update)
+	double *pos = nullptr, *vel = nullptr, *ds = nullptr, *eps = nullptr;   // views into `in`: pos[2n] = x0 y0 x1 y1 ...
 	double *force = nullptr, *irho = nullptr, *imom = nullptr;
 	int32_t *scount = nullptr, *sidx = nullptr, *sjdx = nullptr;
 	double *sdirac = nullptr;
 	int32_t *next = nullptr;          // cell-list links (ordered spread)
 	int32_t *err = nullptr;           // device flag: support overflow
-	double *h_stage = nullptr;        // pinned host staging, 6*cap doubles
+	double *h_stage = nullptr;        // pinned host staging: 6*cap doubles up, 2*cap doubles down
 	int64_t h_cap = 0;
+	cudaEvent_t ev_stage = nullptr;   // completion of the last upload out of h_stage
+	bool stage_busy = false;
 };
 
 }  // namespace life
@@ -108,6 +111,8 @@ struct life_ctx {
 	double *scratch = nullptr;            // device staging for upload / download
 	size_t scratch_bytes = 0;
 	double *d_red = nullptr;              // reduction scratch (max speed etc.)
+	void *eps_buf = nullptr;              // epsilon assembly / LU scratch (ibm_eps.cu)
+	size_t eps_bytes = 0;
 	void *h_pin = nullptr;                // small pinned host buffer
 	size_t h_pin_bytes = 0;
 
@@ -159,7 +164,11 @@ int ibm_set_markers(life_ctx *ctx, int64_t n, const double *pos, const double *v
 int ibm_interp(life_ctx *ctx, double *force_out);
 int ibm_spread(life_ctx *ctx);
 int ibm_clear_force(life_ctx *ctx);
+int ibm_check(life_ctx *ctx);
 void ibm_free(life_ctx *ctx);
+// ibm_eps.cu
+int ibm_compute_epsilon(life_ctx *ctx, int64_t nb, const int64_t *first, const int64_t *members, double *eps_out);
+int ibm_assemble_epsilon(life_ctx *ctx, int64_t nb, const int64_t *first, const int64_t *members, double *A_out);
 
 StepScalars step_scalars(life_ctx *ctx, int32_t t);
 

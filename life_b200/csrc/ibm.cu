@@ -36,16 +36,17 @@ static int ensure_markers(life_ctx *ctx, int64_t n) {
 	int64_t cap = m.cap ? m.cap : 256;
 	while (cap < n) cap *= 2;
 	// contents need not survive a growth: the caller is about to overwrite everything
-	cudaFree(m.pos); cudaFree(m.vel); cudaFree(m.ds); cudaFree(m.eps); cudaFree(m.force); cudaFree(m.irho); cudaFree(m.imom);
+	LIFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	cudaFree(m.in); cudaFree(m.force); cudaFree(m.irho); cudaFree(m.imom);
 	cudaFree(m.scount); cudaFree(m.sidx); cudaFree(m.sjdx); cudaFree(m.sdirac); cudaFree(m.next);
 	if (m.h_stage) cudaFreeHost(m.h_stage);
 	int32_t *keep_err = m.err;
+	cudaEvent_t keep_ev = m.ev_stage;
 	m = MarkerBuffers{};
 	m.err = keep_err;
-	LIFE_CUDA(ctx, cudaMalloc(&m.pos, sizeof(double) * 2 * cap));
-	LIFE_CUDA(ctx, cudaMalloc(&m.vel, sizeof(double) * 2 * cap));
-	LIFE_CUDA(ctx, cudaMalloc(&m.ds, sizeof(double) * cap));
-	LIFE_CUDA(ctx, cudaMalloc(&m.eps, sizeof(double) * cap));
+	m.ev_stage = keep_ev;
+	// pos | vel | ds | eps live in ONE device array laid out like the pinned staging buffer, so a marker update is one copy
+	LIFE_CUDA(ctx, cudaMalloc(&m.in, sizeof(double) * 6 * cap));
 	LIFE_CUDA(ctx, cudaMalloc(&m.force, sizeof(double) * 2 * cap));
 	LIFE_CUDA(ctx, cudaMalloc(&m.irho, sizeof(double) * cap));
 	LIFE_CUDA(ctx, cudaMalloc(&m.imom, sizeof(double) * 2 * cap));
@@ -56,21 +57,23 @@ static int ensure_markers(life_ctx *ctx, int64_t n) {
 	LIFE_CUDA(ctx, cudaMalloc(&m.next, sizeof(int32_t) * cap));
 	LIFE_CUDA(ctx, cudaMemsetAsync(m.force, 0, sizeof(double) * 2 * cap, ctx->stream));
 	LIFE_CUDA(ctx, cudaMemsetAsync(m.scount, 0, sizeof(int32_t) * cap, ctx->stream));
-	LIFE_CUDA(ctx, cudaMallocHost(&m.h_stage, sizeof(double) * 6 * cap));
+	LIFE_CUDA(ctx, cudaMallocHost(&m.h_stage, sizeof(double) * 8 * cap));   // 6*cap upload staging + 2*cap result staging
 	m.h_cap = cap;
 	m.cap = cap;
 	if (!ctx->mk.err) {
 		LIFE_CUDA(ctx, cudaMalloc(&ctx->mk.err, sizeof(int32_t)));
 		LIFE_CUDA(ctx, cudaMemsetAsync(ctx->mk.err, 0, sizeof(int32_t), ctx->stream));
 	}
+	if (!ctx->mk.ev_stage) LIFE_CUDA(ctx, cudaEventCreateWithFlags(&ctx->mk.ev_stage, cudaEventDisableTiming));
 	return LIFE_OK;
 }
 
 void ibm_free(life_ctx *ctx) {
 	MarkerBuffers &m = ctx->mk;
-	cudaFree(m.pos); cudaFree(m.vel); cudaFree(m.ds); cudaFree(m.eps); cudaFree(m.force); cudaFree(m.irho); cudaFree(m.imom);
+	cudaFree(m.in); cudaFree(m.force); cudaFree(m.irho); cudaFree(m.imom);
 	cudaFree(m.scount); cudaFree(m.sidx); cudaFree(m.sjdx); cudaFree(m.sdirac); cudaFree(m.next); cudaFree(m.err);
 	if (m.h_stage) cudaFreeHost(m.h_stage);
+	if (m.ev_stage) cudaEventDestroy(m.ev_stage);
 	m = MarkerBuffers{};
 }
 
@@ -158,30 +161,46 @@ int ibm_set_markers(life_ctx *ctx, int64_t n, const double *pos, const double *v
 	if ((rc = ensure_markers(ctx, n))) return rc;
 	MarkerBuffers &m = ctx->mk;
 	m.n = n;
+	m.pos = m.in; m.vel = m.in + 2 * n; m.ds = m.in + 4 * n; m.eps = m.in + 5 * n;
 	if (n == 0) return LIFE_OK;
-	LIFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // staging buffer may still be in flight from the previous call
+	// the staging buffer may still be feeding the previous update's copy
+	if (m.stage_busy) LIFE_CUDA(ctx, cudaEventSynchronize(m.ev_stage));
 	double *h = m.h_stage;
 	memcpy(h, pos, sizeof(double) * 2 * n);
 	memcpy(h + 2 * n, vel, sizeof(double) * 2 * n);
 	memcpy(h + 4 * n, ds, sizeof(double) * n);
 	memcpy(h + 5 * n, eps, sizeof(double) * n);
-	LIFE_CUDA(ctx, cudaMemcpyAsync(m.pos, h, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, ctx->stream));
-	LIFE_CUDA(ctx, cudaMemcpyAsync(m.vel, h + 2 * n, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, ctx->stream));
-	LIFE_CUDA(ctx, cudaMemcpyAsync(m.ds, h + 4 * n, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
-	LIFE_CUDA(ctx, cudaMemcpyAsync(m.eps, h + 5 * n, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+	LIFE_CUDA(ctx, cudaMemcpyAsync(m.in, h, sizeof(double) * 6 * n, cudaMemcpyHostToDevice, ctx->stream));
+	LIFE_CUDA(ctx, cudaEventRecord(m.ev_stage, ctx->stream));
+	m.stage_busy = true;
 	const int64_t threads = n * 32;
 	k_find_support<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(n, m.pos, ctx->cfg.Dx, ctx->cfg.Nx, ctx->cfg.Ny,
 	                                                                           m.scount, m.sidx, m.sjdx, m.sdirac, m.err);
 	ctx->launches++;
 	LIFE_CUDA(ctx, cudaGetLastError());
-	int32_t *herr = reinterpret_cast<int32_t *>(ctx->h_pin);
-	LIFE_CUDA(ctx, cudaMemcpyAsync(herr, m.err, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-	LIFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-	if (*herr & 1) {
-		LIFE_CUDA(ctx, cudaMemsetAsync(m.err, 0, sizeof(int32_t), ctx->stream));
+	// asynchronous: a support overflow (src/IBMNode.cpp:171-172) is reported by the next synchronising marker call
+	return LIFE_OK;
+}
+
+// reads back the device error flag (after a synchronisation of ctx->stream has been enqueued by the caller)
+static int check_marker_errors(life_ctx *ctx, const int32_t *host_flag) {
+	if (*host_flag & 1) {
+		LIFE_CUDA(ctx, cudaMemsetAsync(ctx->mk.err, 0, sizeof(int32_t), ctx->stream));
 		return fail(ctx, LIFE_E_SUPPORT, "Support buffer size is not big enough for number of support points");
 	}
+	if (*host_flag & 2) {
+		LIFE_CUDA(ctx, cudaMemsetAsync(ctx->mk.err, 0, sizeof(int32_t), ctx->stream));
+		return fail(ctx, LIFE_E_SUPPORT, "ordered spread: more than 32 markers contribute to one lattice site");
+	}
 	return LIFE_OK;
+}
+
+int ibm_check(life_ctx *ctx) {
+	if (!ctx->mk.err) return LIFE_OK;
+	int32_t *herr = reinterpret_cast<int32_t *>(ctx->h_pin);
+	LIFE_CUDA(ctx, cudaMemcpyAsync(herr, ctx->mk.err, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+	LIFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return check_marker_errors(ctx, herr);
 }
 
 // ---- interpolation + force ------------------------------------------------------------------------------------------------------
@@ -284,14 +303,19 @@ int ibm_interp(life_ctx *ctx, double *force_out) {
 		ctx->launches++;
 		LIFE_CUDA(ctx, cudaGetLastError());
 	}
+	int32_t *herr = reinterpret_cast<int32_t *>(ctx->h_pin);
+	LIFE_CUDA(ctx, cudaMemcpyAsync(herr, m.err, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
 	if (force_out) {
-		LIFE_CUDA(ctx, cudaMemcpyAsync(m.h_stage, m.force, sizeof(double) * 2 * m.n, cudaMemcpyDeviceToHost, ctx->stream));
+		// results come back through the second half of the pinned staging buffer (the first half may feed an upload)
+		double *hf = m.h_stage + 6 * m.h_cap;
+		LIFE_CUDA(ctx, cudaMemcpyAsync(hf, m.force, sizeof(double) * 2 * m.n, cudaMemcpyDeviceToHost, ctx->stream));
 		LIFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-		memcpy(force_out, m.h_stage, sizeof(double) * 2 * m.n);
+		memcpy(force_out, hf, sizeof(double) * 2 * m.n);
 	} else {
 		LIFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	}
-	return LIFE_OK;
+	m.stage_busy = false;
+	return check_marker_errors(ctx, herr);
 }
 
 // ---- spread ------------------------------------------------------------------------------------------------------------------------

@@ -7,6 +7,13 @@
 //   GridClass::lbmKernel()            (src/Grid.cpp:36-100)     -> life_step
 //   ObjectsClass::ibmKernelInterp()   (src/Objects.cpp:102-117) -> life_ibm_set_markers + life_ibm_interp
 //   ObjectsClass::ibmKernelSpread()   (src/Objects.cpp:120-149) -> life_ibm_spread
+//   ObjectsClass::computeEpsilon()    (src/Objects.cpp:235-321), ONLY when the environment sets LIFE_B200_DEVICE_EPSILON
+//                                     (by default the reference's own host code runs, as the north star
+//                                     prescribes):  =1 -> life_ibm_assemble_epsilon (matrix on the GPU, bit-exact) + the
+//                                     reference's own Utils::solveLAPACK on the host (epsilon bit-identical to the reference);
+//                                     =2 -> life_ibm_compute_epsilon (assembly and LU both on the GPU);
+//                                     =3 -> per body: GPU LU for small systems (<= 64 markers, many of them: Honami), GPU
+//                                     assembly + host LAPACK for large ones (UNI_EPSILON: TurekHron 132, PELskin 310)
 //   GridClass::writeInfo / writeVTK / writeRestart (src/Grid.cpp:559, :790, :1163): refresh the host mirrors
 //                                     (life_download_macro / life_download_state), then run the reference's own writer
 //
@@ -30,6 +37,7 @@
 #include "Utils.h"
 #include "life_b200.h"
 #include <dlfcn.h>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 
@@ -40,8 +48,19 @@ struct DeviceSide {
 	bool macro_stale = false;    // host rho / u are older than the device state
 	bool full_stale = false;     // host f / force_ibm are older than the device state
 	std::vector<double> pos, vel, ds, eps, force;   // marker staging (SoA)
-	long steps = 0, interps = 0, spreads = 0;
+	long steps = 0, interps = 0, spreads = 0, eps_solves = 0;
+	std::vector<int64_t> grp_first, grp_members;
+	std::vector<double> eps_mat;
+	// wall-clock accounting (seconds spent inside each replaced body; the rest of the program is the reference's host code)
+	double t_step = 0, t_interp = 0, t_spread = 0, t_eps = 0, t_io = 0, t_first = 0, t_begin = 0;
 } dev;
+
+double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+struct Timed {
+	double &acc, t0;
+	explicit Timed(double &a) : acc(a), t0(now()) {}
+	~Timed() { acc += now() - t0; }
+};
 
 [[noreturn]] void die(const char *where, int rc) {
 	ERROR(std::string("liblife_b200: ") + where + " failed (" + std::to_string(rc) + "): " + life_last_error(dev.ctx));
@@ -106,8 +125,17 @@ life_config make_config(const GridClass &g) {
 void report() {
 	if (!dev.ctx) return;
 	life_sync(dev.ctx);
-	std::fprintf(stderr, "\n[life_b200] %ld life_step, %ld life_ibm_interp, %ld life_ibm_spread, %lld kernel launches\n", dev.steps,
-	             dev.interps, dev.spreads, (long long)life_launch_count(dev.ctx));
+	const double wall = now() - dev.t_begin;
+	std::fprintf(stderr, "\n[life_b200] wall %.3f s since the first step, of which first step (context + upload) %.3f s; inside life_step %.3f s, "
+	                     "interp %.3f s, spread %.3f s, epsilon %.3f s, download+writers %.3f s; remaining host code %.3f s",
+	             wall, dev.t_first, dev.t_step, dev.t_interp, dev.t_spread, dev.t_eps, dev.t_io,
+	             wall - dev.t_first - dev.t_step - dev.t_interp - dev.t_spread - dev.t_eps - dev.t_io);
+	if (dev.steps > 1)
+		std::fprintf(stderr, "\n[life_b200] steady state %.1f us per time step = %.1f MLUPS (%ld x %ld lattice, steps 2..%ld, all host work and output included)",
+		             1e6 * (wall - dev.t_first) / (double)(dev.steps - 1), (double)Nx * Ny * (dev.steps - 1) / (wall - dev.t_first) / 1e6,
+		             (long)Nx, (long)Ny, dev.steps);
+	std::fprintf(stderr, "\n[life_b200] %ld life_step, %ld life_ibm_interp, %ld life_ibm_spread, %ld life_ibm_compute_epsilon, %lld kernel launches\n",
+	             dev.steps, dev.interps, dev.spreads, dev.eps_solves, (long long)life_launch_count(dev.ctx));
 	life_destroy(dev.ctx);
 	dev.ctx = nullptr;
 }
@@ -123,6 +151,9 @@ Fn next_symbol(const char *mangled) {
 
 // ---- GridClass::lbmKernel -------------------------------------------------------------------------------------------------------
 void GridClass::lbmKernel() {
+	const bool first = !dev.ctx;
+	if (first) dev.t_begin = now();
+	Timed timed(first ? dev.t_first : dev.t_step);
 	if (!dev.ctx) {
 		// first step (fresh start or just after readRestart): hand over what initialiseGrid / readRestart produced
 		const life_config c = make_config(*this);
@@ -138,8 +169,10 @@ void GridClass::lbmKernel() {
 	dev.macro_stale = dev.full_stale = true;
 }
 
-// ---- ObjectsClass::ibmKernelInterp ----------------------------------------------------------------------------------------------
-void ObjectsClass::ibmKernelInterp() {
+namespace {
+// iNode[i].pos / vel / ds / epsilon -> SoA staging -> device; the device rebuilds every marker's support from pos exactly as
+// the host's findSupport did (bit-exact map)
+void send_markers(std::vector<IBMNodeClass> &iNode) {
 	const size_t n = iNode.size();
 	dev.pos.resize(2 * n); dev.vel.resize(2 * n); dev.ds.resize(n); dev.eps.resize(n); dev.force.resize(2 * n);
 	for (size_t i = 0; i < n; i++) {
@@ -148,8 +181,75 @@ void ObjectsClass::ibmKernelInterp() {
 		dev.ds[i] = iNode[i].ds;
 		dev.eps[i] = iNode[i].epsilon;
 	}
-	// the device rebuilds every marker's support from pos exactly as the host's findSupport did (bit-exact map)
 	LIFE_CK(life_ibm_set_markers(dev.ctx, (int64_t)n, dev.pos.data(), dev.vel.data(), dev.ds.data(), dev.eps.data()));
+}
+}  // namespace
+
+// ---- ObjectsClass::computeEpsilon (optional) ----------------------------------------------------------------------------------------
+void ObjectsClass::computeEpsilon() {
+	Timed timed(dev.t_eps);
+	static const int on_device = [] { const char *e = std::getenv("LIFE_B200_DEVICE_EPSILON"); return e ? std::atoi(e) : 0; }();
+	if (!on_device || !dev.ctx) {
+		// default, and always during construction (t = 0, before the first step creates the context): the reference's own
+		// assembly + LAPACK solve
+		using Fn = void (*)(ObjectsClass *);
+		static Fn orig = next_symbol<Fn>("_ZN12ObjectsClass14computeEpsilonEv");
+		orig(this);
+		return;
+	}
+	// marker groups exactly as src/Objects.cpp:238-262 forms them: every marker in one body under UNI_EPSILON (that temporary
+	// body counts as flexible), otherwise one group per flexible body (t > 0 here, so rigid bodies keep their epsilon)
+	dev.grp_first.assign(1, 0);
+	dev.grp_members.clear();
+#ifdef UNI_EPSILON
+	for (size_t i = 0; i < iNode.size(); i++) dev.grp_members.push_back((int64_t)i);
+	dev.grp_first.push_back((int64_t)dev.grp_members.size());
+#else
+	for (size_t ib = 0; ib < iBody.size(); ib++) {
+		if (iBody[ib].flex != eFlexible) continue;
+		for (size_t k = 0; k < iBody[ib].node.size(); k++) dev.grp_members.push_back((int64_t)(iBody[ib].node[k] - &iNode[0]));
+		dev.grp_first.push_back((int64_t)dev.grp_members.size());
+	}
+#endif
+	send_markers(iNode);
+	// split the groups by where their LU runs
+	std::vector<int64_t> dfirst(1, 0), dmem, hfirst(1, 0), hmem;
+	const int64_t nb = (int64_t)dev.grp_first.size() - 1;
+	for (int64_t b = 0; b < nb; b++) {
+		const int64_t lo = dev.grp_first[b], hi = dev.grp_first[b + 1];
+		const bool lu_on_device = on_device == 2 || (on_device == 3 && hi - lo <= 64);
+		std::vector<int64_t> &first = lu_on_device ? dfirst : hfirst, &mem = lu_on_device ? dmem : hmem;
+		mem.insert(mem.end(), dev.grp_members.begin() + lo, dev.grp_members.begin() + hi);
+		first.push_back((int64_t)mem.size());
+	}
+	if (dfirst.size() > 1) {
+		LIFE_CK(life_ibm_compute_epsilon(dev.ctx, (int64_t)dfirst.size() - 1, dfirst.data(), dmem.data(), dev.eps.data()));
+		for (size_t k = 0; k < dmem.size(); k++) iNode[(size_t)dmem[k]].epsilon = dev.eps[(size_t)dmem[k]];
+	}
+	if (hfirst.size() > 1) {
+		// matrices from the GPU, then exactly src/Objects.cpp:303-311: b = 1, Utils::solveLAPACK, scatter to the markers
+		const int64_t nh = (int64_t)hfirst.size() - 1;
+		std::vector<size_t> off((size_t)nh + 1, 0);
+		for (int64_t b = 0; b < nh; b++) { const size_t d = (size_t)(hfirst[b + 1] - hfirst[b]); off[(size_t)b + 1] = off[(size_t)b] + d * d; }
+		dev.eps_mat.resize(off[(size_t)nh]);
+		LIFE_CK(life_ibm_assemble_epsilon(dev.ctx, nh, hfirst.data(), hmem.data(), dev.eps_mat.data()));
+#pragma omp parallel for schedule(guided)
+		for (int64_t b = 0; b < nh; b++) {
+			const size_t d = (size_t)(hfirst[b + 1] - hfirst[b]);
+			std::vector<double> A(dev.eps_mat.begin() + off[(size_t)b], dev.eps_mat.begin() + off[(size_t)b + 1]);
+			std::vector<double> rhs(d, 1.0);
+			const std::vector<double> sol = Utils::solveLAPACK(A, rhs);
+			for (size_t i = 0; i < d; i++) iNode[(size_t)hmem[(size_t)hfirst[b] + i]].epsilon = sol[i];
+		}
+	}
+	dev.eps_solves++;
+}
+
+// ---- ObjectsClass::ibmKernelInterp ----------------------------------------------------------------------------------------------
+void ObjectsClass::ibmKernelInterp() {
+	Timed timed(dev.t_interp);
+	const size_t n = iNode.size();
+	send_markers(iNode);
 	LIFE_CK(life_ibm_interp(dev.ctx, dev.force.data()));
 	for (size_t i = 0; i < n; i++) {
 		iNode[i].force[eX] = dev.force[2 * i];      // consumed by the host FEM (src/FEMElement.cpp:53) and writeTotalForces
@@ -163,6 +263,7 @@ void ObjectsClass::ibmKernelInterp() {
 void ObjectsClass::ibmKernelSpread() {
 	// supports, ds, epsilon: those of the last ibmKernelInterp (the host recomputes them only in recomputeObjectVals, which
 	// always precedes an interp); forces: those the last interp left on the device
+	Timed timed(dev.t_spread);
 	LIFE_CK(life_ibm_spread(dev.ctx));
 	dev.spreads++;
 	dev.macro_stale = dev.full_stale = true;
@@ -170,6 +271,7 @@ void ObjectsClass::ibmKernelSpread() {
 
 // ---- output: refresh the host mirrors, then the reference's own writers ------------------------------------------------------------
 void GridClass::writeInfo() {
+	Timed timed(dev.t_io);
 	if (dev.ctx && dev.macro_stale) {
 		LIFE_CK(life_download_macro(dev.ctx, rho.data(), u.data()));
 		dev.macro_stale = false;
@@ -180,6 +282,7 @@ void GridClass::writeInfo() {
 }
 
 void GridClass::writeVTK() {
+	Timed timed(dev.t_io);
 	if (dev.ctx && dev.macro_stale) {
 		LIFE_CK(life_download_macro(dev.ctx, rho.data(), u.data()));
 		dev.macro_stale = false;
@@ -190,6 +293,7 @@ void GridClass::writeVTK() {
 }
 
 void GridClass::writeRestart() {
+	Timed timed(dev.t_io);
 	if (dev.ctx && dev.full_stale) {
 		LIFE_CK(life_download_state(dev.ctx, f.data(), rho.data(), u.data(), force_ibm.data()));
 		dev.full_stale = dev.macro_stale = false;

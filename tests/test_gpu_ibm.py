@@ -152,3 +152,100 @@ def test_support_overflow_is_reported():
     f = ctx.ibm_interp()
     assert f.shape == (n, 2) and np.isfinite(f).all()
     ctx.close()
+
+
+def _groups(g):
+    """marker groups of computeEpsilon: one group with every marker under UNI_EPSILON, else one per body (Objects.cpp:238-251)"""
+    n = len(g["m_ds"])
+    if int(g["uni_epsilon"]):
+        return [np.arange(n)]
+    body = g["m_body"]
+    return [np.nonzero(body == b)[0] for b in np.unique(body)]
+
+
+@pytest.mark.parametrize("case", K.EXAMPLES_IBM)
+def test_device_epsilon_matches_lapack(case):
+    """life_ibm_compute_epsilon (optional device path of computeEpsilon + solveLAPACK) against the epsilon the compiled
+    reference obtained from LAPACK: at t = 0 for every body, and along the recorded FSI trace for the flexible ones."""
+    from life_b200 import capi
+    g = K.golden(case)
+    o = K.make_oracle(g)
+    ctx = capi.Context(K.life_config(o.params, o))
+    n = len(g["m_ds"])
+    groups = _groups(g)
+    ctx.ibm_set_markers(g["m_pos"], g["m_vel"], g["m_ds"], np.zeros(n))
+    eps = ctx.ibm_compute_epsilon(groups)
+    assert K.rel_l2(eps, g["m_eps"]) < K.TOL, K.rel_l2(eps, g["m_eps"])
+    # the value is also what the device now spreads with
+    _, _, _, _ = ctx.ibm_get_supports()
+    # along the trace: the reference recomputes epsilon of flexible bodies (all markers under UNI_EPSILON) every sub-iteration
+    flex = g["m_flex"] == 0      # eFlexible = 0 (inc/defs.h:49)
+    if int(g["uni_epsilon"]):
+        flex = np.ones(n, bool) if flex.any() else flex
+    if flex.any():
+        sel = [grp for grp in groups if flex[grp].all()]
+        worst = 0.0
+        for k in range(0, len(g["trace_step"]), max(1, len(g["trace_step"]) // 8)):
+            ctx.ibm_set_markers(g["trace_pos"][k], g["trace_vel"][k], g["trace_ds"][k], g["trace_eps"][k])
+            eps = ctx.ibm_compute_epsilon(sel)
+            worst = max(worst, K.rel_l2(eps, g["trace_eps"][k]))
+        assert worst < K.TOL, worst
+    ctx.close()
+
+
+def test_device_epsilon_groups_and_errors():
+    from life_b200 import capi
+    g = K.golden("Cylinder")
+    o = K.make_oracle(g)
+    ctx = capi.Context(K.life_config(o.params, o))
+    n = len(g["m_ds"])
+    start = np.linspace(0.5, 0.9, n)
+    ctx.ibm_set_markers(g["m_pos"], g["m_vel"], g["m_ds"], start)
+    # no groups: nothing changes; a subset: only its members change
+    assert np.array_equal(ctx.ibm_compute_epsilon([]), start)
+    half = np.arange(0, n, 2)
+    eps = ctx.ibm_compute_epsilon([half])
+    rest = np.setdiff1d(np.arange(n), half)
+    assert np.array_equal(eps[rest], start[rest])
+    assert not np.array_equal(eps[half], start[half]) and np.isfinite(eps).all()
+    # oracle: same subset as one body
+    o.set_markers(g["m_pos"][half], g["m_vel"][half], g["m_ds"][half], start[half])
+    o.find_support()
+    o.compute_epsilon(0, len(half))
+    assert K.rel_l2(eps[half], o.ds_eps()[1]) < K.TOL
+    with pytest.raises(capi.LifeError) as e:
+        ctx.ibm_compute_epsilon([np.array([0, n + 3])])
+    assert e.value.code == capi.E_ARG
+    ctx.close()
+
+
+def test_device_epsilon_matrix_is_bit_exact():
+    """life_ibm_assemble_epsilon returns the matrix computeEpsilon builds (src/Objects.cpp:262-301), bit for bit: rebuilt here
+    term by term in the reference's order from the oracle's supports and delta function."""
+    from life_b200 import capi
+    from oracle import oracle as O
+    g = K.golden("Cylinder")
+    o = K.make_oracle(g)
+    n = len(g["m_ds"])
+    ctx = capi.Context(K.life_config(o.params, o))
+    ctx.ibm_set_markers(g["m_pos"], g["m_vel"], g["m_ds"], g["m_eps"])
+    A = ctx.ibm_assemble_epsilon([np.arange(n)])[0]
+    o.set_markers(g["m_pos"], g["m_vel"], g["m_ds"], g["m_eps"])
+    o.find_support()
+    cnt, idx, jdx, dirac = o.supports()
+    dd = O.lib().orc_dirac_delta
+    pos, ds, Dx = g["m_pos"], g["m_ds"], o.Dx
+    want = np.zeros((n, n))
+    for i in range(n):
+        for j in range(n):
+            acc = 0.0
+            for s in range(cnt[i]):
+                dj = dd(abs(pos[j, 0] / Dx - idx[i, s])) * dd(abs(pos[j, 1] / Dx - jdx[i, s]))
+                acc += dirac[i, s] * dj
+            want[i, j] = acc * (1.0 * 1.0 * ds[j])
+    assert np.array_equal(A, want)
+    # and the host's LAPACK on that matrix gives the reference's epsilon
+    import scipy.linalg as sl
+    eps = sl.solve(A, np.ones(n))
+    assert K.rel_l2(eps, g["m_eps"]) < 1e-12
+    ctx.close()

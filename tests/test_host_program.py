@@ -5,6 +5,7 @@ path, then compare Results/), with `diff -r` relaxed to the north-star tolerance
 relative L2 1e-10.  The host-side FEM / LAPACK epsilon solve / Aitken loop run live in both programs.
 """
 import os
+import re
 import shutil
 import subprocess
 
@@ -22,15 +23,17 @@ def _have(case, exe):
     return os.path.exists(os.path.join(HOST, case, exe))
 
 
-def _run(case, exe, workdir, times=1):
+def _run(case, exe, workdir, times=1, **extra_env):
     os.makedirs(workdir, exist_ok=True)
     inp = os.path.join(HOST, case, "input")
     if os.path.isdir(inp):
         shutil.copytree(inp, os.path.join(workdir, "input"), dirs_exist_ok=True)
-    env = dict(os.environ, OPENBLAS_NUM_THREADS="1")
+    env = dict(os.environ, OPENBLAS_NUM_THREADS="1", **extra_env)
     for _ in range(times):
         p = subprocess.run([os.path.join(HOST, case, exe)], cwd=workdir, env=env, stdout=subprocess.PIPE,
                            stderr=subprocess.PIPE, text=True, timeout=1200)
+    m = re.search(r"Simulation took ([0-9.]+) seconds", p.stdout)          # main.cpp:93, includes construction and all I/O
+    p.seconds = float(m.group(1)) if m else float("nan")
     return p
 
 
@@ -60,16 +63,22 @@ def _compare(case, ref_dir, new_dir):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("device_eps", [0, 1, 2, 3], ids=["host-eps", "device-assembly+lapack", "device-eps", "auto-eps"])
 @pytest.mark.parametrize("case", EXAMPLES)
-def test_program_reproduces_reference_results(case, tmp_path):
+def test_program_reproduces_reference_results(case, device_eps, tmp_path):
     if not (_have(case, "LIFE_b200") and _have(case, "LIFE_ref")):
         pytest.skip("life_b200/host/_build/%s not built (make -C life_b200/host needs /root/reference)" % case)
+    if device_eps and case not in FLEXIBLE:
+        pytest.skip("epsilon is only recomputed for flexible bodies")
     times = 2 if case == "TurekHron" else 1          # second run restarts from Results/Restart (store-ref-data.sh:51-53)
     ref = _run(case, "LIFE_ref", str(tmp_path / "ref"), times)
     assert ref.returncode == 0, ref.stdout[-2000:]
-    new = _run(case, "LIFE_b200", str(tmp_path / "b200"), times)
+    new = _run(case, "LIFE_b200", str(tmp_path / "b200"), times, LIFE_B200_DEVICE_EPSILON=str(device_eps))
     assert new.returncode == 0, new.stdout[-2000:] + new.stderr[-2000:]
     assert "life_step" in new.stderr and " 0 life_step" not in new.stderr      # the CUDA path really ran
+    assert (" 0 life_ibm_compute_epsilon" in new.stderr) == (not device_eps)
+    print("\n%s wall time of the last run (500 steps incl. all host work and I/O): LIFE_ref %.2f s (%d host threads), LIFE_b200 %.2f s   %s"
+          % (case, ref.seconds, os.cpu_count(), new.seconds, new.stderr.strip().splitlines()[-1]))
     t_end, err = _compare(case, str(tmp_path / "ref"), str(tmp_path / "b200"))
     assert t_end == 500 * times
     assert sorted(os.listdir(tmp_path / "ref" / "Results" / "VTK")) == sorted(os.listdir(tmp_path / "b200" / "Results" / "VTK"))

@@ -235,6 +235,8 @@ def run_gpu_arm(args):
 
     S, K, W = args.size, args.steps, args.warmup
     Nx, Ny = S * world, S
+    if args.global_nx > 0:          # strong scaling: the global lattice is fixed and cut into `world` slabs
+        Nx = args.global_nx
     coll = capi.CENTRAL_MOMENTS if args.collision == "cm" else capi.BGK
     # the reference's scalings for this case (src/Grid.cpp:1257-1260 with height_p = 1, omega = 1, lid 0.1 lattice units)
     Dx = 1.0 / (Ny - 1)
@@ -406,9 +408,9 @@ def run_gpu_arm(args):
         return 0
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong" if args.global_nx > 0 else "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": workload_config(S, world, args.collision),
+        "config": dict(workload_config(S, world, args.collision), Nx=Nx, **({"workload": "synthetic lid-driven cavity, global lattice %dx%d cut into %d x-slabs (strong scaling)" % (Nx, Ny, world)} if args.global_nx > 0 else {})),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                      "kernel": "k_bulk (fused stream+collide sweep)", "kernel_ms": bulk_ms, "launches_timed": bulk_n,
@@ -436,6 +438,8 @@ def main():
     ap.add_argument("--size", type=int, default=16384, help="lattice nodes per side per GPU")
     ap.add_argument("--collision", default="bgk", choices=["bgk", "cm"])
     ap.add_argument("--kernel", type=int, default=0, help="LIFE_KERNEL_* (0 = auto)")
+    ap.add_argument("--global-nx", type=int, default=0,
+                    help="strong scaling: fix the global lattice at GLOBAL_NX x SIZE and cut it into --gpus slabs (default: weak scaling, SIZE x SIZE per GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--host-chunk-columns", type=int, default=0,
                     help="stream the host image through life_upload_columns / life_download_columns in ranges of this many "

@@ -164,8 +164,144 @@ __global__ void __launch_bounds__(BLOCK) k_bulk_shuffle(const BulkArgs a) {
 	}
 }
 
+// ---- TMA: persistent CTAs, populations prefetched through shared memory by bulk asynchronous copies -----------------------------
+// 2 CTAs per SM stay resident for the whole sweep and walk the (column, 512-row tile) list with stride gridDim.x.  One elected
+// thread arms an mbarrier with the tile's byte count and issues nine cp.async.bulk copies (one contiguous 4 KB run per plane:
+// SoA + y-fastest layout means a tile of a plane IS a contiguous run, so the 1-D bulk form needs no tensor map); the copies of
+// the next TMA_STAGES-1 tiles are in flight while the current one is collided.  Stores leave from registers exactly as in the
+// SHUFFLE variant.  SASS: UBLKCP.S.G + SYNCS (mbarrier), no LDG on the population path.
+constexpr int TMA_TILE = 512;      // rows per tile = 2 per thread
+constexpr int TMA_STAGES = 3;
+constexpr int TMA_SMEM_BYTES = TMA_STAGES * NV * TMA_TILE * 8 + TMA_STAGES * 8;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+	             "l"(src), "r"(bytes), "r"(smem_u32(bar))
+	             : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+	asm volatile(
+	    "{\n"
+	    ".reg .pred P1;\n"
+	    "LIFE_WAIT:\n"
+	    "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+	    "@P1 bra LIFE_DONE;\n"
+	    "bra LIFE_WAIT;\n"
+	    "LIFE_DONE:\n"
+	    "}" ::"r"(smem_u32(bar)),
+	    "r"(parity)
+	    : "memory");
+}
+
+template <int COLL, int MODE>
+__global__ void __launch_bounds__(256, 2) k_bulk_tma(const BulkArgs a, const int64_t n_tiles) {
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	double *buf = reinterpret_cast<double *>(smem_raw);                                   // [stage][plane][row]
+	uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + TMA_STAGES * NV * TMA_TILE * 8);
+	const int tid = threadIdx.x, lane = tid & 31;
+
+	if (tid == 0) {
+		for (int s = 0; s < TMA_STAGES; s++) mbar_init(&full[s], 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+
+	// elected thread: arm the stage's barrier and start the nine plane copies of `tile`
+	auto issue = [&](int64_t tile, int s) {
+		const int64_t col = a.c_first + tile / a.tiles;
+		const int64_t j0 = (tile % a.tiles) * TMA_TILE;
+		int64_t rows = a.L.P - JOFF - j0;             // never run past the end of this column's pitch
+		if (rows > TMA_TILE) rows = TMA_TILE;
+		const unsigned bytes = (unsigned)(rows * 8);   // P, JOFF, j0 are multiples of 16 rows: 16-byte granular
+		const int64_t idx0 = col * a.L.P + j0 + JOFF;
+		mbar_expect_tx(&full[s], bytes * NV);
+#pragma unroll
+		for (int v = 0; v < NV; v++) bulk_g2s(buf + (s * NV + v) * TMA_TILE, a.fin + v * a.L.S + idx0, bytes, &full[s]);
+	};
+
+	if (tid == 0)
+		for (int s = 0; s < TMA_STAGES; s++) {
+			const int64_t tile = (int64_t)blockIdx.x + (int64_t)s * gridDim.x;
+			if (tile < n_tiles) issue(tile, s);
+		}
+
+	int s = 0;
+	unsigned phase = 0;
+	for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+		const int64_t col = a.c_first + tile / a.tiles;
+		const int64_t j = (tile % a.tiles) * TMA_TILE + 2 * tid;
+		mbar_wait(&full[s], phase);
+		double f0[NV], f1[NV], o0[NV], o1[NV];
+#pragma unroll
+		for (int v = 0; v < NV; v++) {
+			const double2 t = *reinterpret_cast<const double2 *>(buf + (s * NV + v) * TMA_TILE + 2 * tid);
+			f0[v] = t.x; f1[v] = t.y;
+		}
+		__syncthreads();                               // every thread has drained this stage: it can be refilled
+		if (tid == 0) {
+			const int64_t next = tile + (int64_t)TMA_STAGES * gridDim.x;
+			if (next < n_tiles) issue(next, s);
+		}
+		if (++s == TMA_STAGES) { s = 0; phase ^= 1; }
+
+		const bool v0ok = j < a.L.Ny, v1ok = j + 1 < a.L.Ny;
+		const int64_t jw = j - 2 * lane;
+		if (jw >= a.L.Ny) continue;                    // whole warp beyond the column (warp-uniform)
+		const int64_t idx = col * a.L.P + j + JOFF;
+		if (v0ok) node_update<COLL, MODE>(a, idx, f0, o0);
+		if (v1ok) node_update<COLL, MODE>(a, idx + 1, f1, o1);
+#pragma unroll
+		for (int v = 0; v < NV; v++) {
+			double *dst = a.fout + v * a.L.S + idx + LIFE_CX(v) * a.L.P;
+			if (LIFE_CY(v) == 0) {
+				if (v1ok) st_pair<0>(dst, o0[v], o1[v]);
+				else if (v0ok) st_one<0>(dst, o0[v]);
+			} else if (LIFE_CY(v) == 1) {
+				const double up = __shfl_up_sync(0xffffffffu, o1[v], 1);
+				if (lane == 0) { if (v0ok) st_one<0>(dst + 1, o0[v]); }
+				else if (v0ok) st_pair<0>(dst, up, o0[v]);
+				else if (j - 1 < a.L.Ny) st_one<0>(dst, up);
+				if (lane == 31 && v1ok) st_one<0>(dst + 2, o1[v]);
+			} else {
+				const double dn = __shfl_down_sync(0xffffffffu, o0[v], 1);
+				if (lane == 0 && v0ok) st_one<0>(dst - 1, o0[v]);
+				if (lane == 31) { if (v1ok) st_one<0>(dst, o1[v]); }
+				else if (j + 2 < a.L.Ny) st_pair<0>(dst, o1[v], dn);
+				else if (v1ok) st_one<0>(dst, o1[v]);
+			}
+		}
+	}
+}
+
+template <int COLL, int MODE>
+static int launch_tma(life_ctx *ctx, BulkArgs a, int64_t c_count, cudaStream_t st) {
+	static bool configured = false;    // per template instance
+	if (!configured) {
+		LIFE_CUDA(ctx, cudaFuncSetAttribute(k_bulk_tma<COLL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM_BYTES));
+		configured = true;
+	}
+	a.tiles = (a.L.Ny + TMA_TILE - 1) / TMA_TILE;
+	const int64_t n_tiles = a.tiles * c_count;
+	if (n_tiles <= 0) return LIFE_OK;
+	int sms = 148;
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+	const int64_t grid = n_tiles < 2 * sms ? n_tiles : 2 * sms;      // persistent: two resident CTAs per SM
+	k_bulk_tma<COLL, MODE><<<(unsigned)grid, 256, TMA_SMEM_BYTES, st>>>(a, n_tiles);
+	ctx->launches++;
+	LIFE_CUDA(ctx, cudaGetLastError());
+	return LIFE_OK;
+}
+
 template <int COLL, int MODE>
 static int launch_one(life_ctx *ctx, const BulkArgs &a0, int64_t c_count, cudaStream_t st) {
+	if (ctx->cfg.kernel == LIFE_KERNEL_TMA) return launch_tma<COLL, MODE>(ctx, a0, c_count, st);
 	BulkArgs a = a0;
 	const bool staged = ctx->cfg.kernel != LIFE_KERNEL_DIRECT;   // AUTO → SHUFFLE
 	// cfg.tune (measurement only, force-free shuffle kernel): tens digit = cache hint, units digit = CTA size 1:128 2:256 3:512

@@ -24,15 +24,19 @@ def main():
     Dx = 1.0 / (N - 1)
     nu_p = (1.0 / 6.0) / (0.1 * (N - 1))
     Dt = Dx * Dx * (1.0 / 6.0 * 1.0000000000000002) / nu_p
-    f = np.empty((N, N, 9))
+    C = min(N, 1024)
+    f = np.empty((C, N, 9))
     f[...] = W
     u_in = np.tile(np.array([[0.1, 0.0]]), (N, 1))
     for coll, cname in ((capi.BGK, "bgk"), (capi.CENTRAL_MOMENTS, "cm")):
-        for kern, kname in ((capi.KERNEL_DIRECT, "direct"), (capi.KERNEL_SHUFFLE, "shuffle")):
+        for kern, kname in ((capi.KERNEL_DIRECT, "direct"), (capi.KERNEL_SHUFFLE, "shuffle"), (capi.KERNEL_TMA, "tma")):
             cfg = capi.Config(Nx=N, Ny=N, omega=1.0, collision=coll, wall_top=capi.VELOCITY, Dx=Dx, Dt=Dt, Dm=Dx ** 3,
                               kernel=kern)
             ctx = capi.Context(cfg)
-            ctx.upload_state(f, None, None, None, None, u_in, None)
+            ctx.upload_begin(u_in, None)
+            for il0 in range(0, N, C):
+                ctx.upload_columns(il0, min(C, N - il0), f[:min(C, N - il0)])
+            ctx.upload_end()
             ctx.step_n(1, 5)
             ctx.sync()
             ctx.set_profiling(True)

@@ -25,7 +25,7 @@ def _run_pair(g, steps, kernel):
     return o, st
 
 
-@pytest.mark.parametrize("kernel", [1, 2], ids=["direct", "shuffle"])
+@pytest.mark.parametrize("kernel", [1, 2, 3], ids=["direct", "shuffle", "tma"])
 @pytest.mark.parametrize("case", K.EXAMPLES_LBM + K.EXTRA)
 def test_fields_match_oracle(case, kernel):
     g = K.golden(case)
@@ -60,7 +60,7 @@ def test_types_and_boundary_list_bit_exact(case):
     ctx.close()
 
 
-@pytest.mark.parametrize("kernel", [1, 2], ids=["direct", "shuffle"])
+@pytest.mark.parametrize("kernel", [1, 2, 3], ids=["direct", "shuffle", "tma"])
 @pytest.mark.parametrize("shape", [(40, 36), (37, 41), (5, 7), (130, 515)])
 def test_push_map_bit_exact(shape, kernel):
     """omega = 0 turns the BGK step into a pure push: tagged populations must land exactly where the reference's

@@ -310,14 +310,15 @@ def run_gpu_arm(args):
         return D.max_over_ranks(x, device=dev)
 
     # ---- device-resident throughput ("value") ------------------------------------------------------------------------
+    # nvidia-smi needs a second or more to start on a multi-GPU box: launch it now, use only the samples inside the timed region
+    uuid = getattr(torch.cuda.get_device_properties(local), "uuid", None)
+    uuid = None if uuid is None else (str(uuid) if str(uuid).startswith("GPU-") else "GPU-" + str(uuid))
+    sampler = ClockSampler(uuid) if rank == 0 else None
     upload()
     ctx.step_n(1, W)
     download_macro()                         # allocates the on-demand macroscopic planes outside any timed region
     t_next = W + 1
     barrier()
-    uuid = getattr(torch.cuda.get_device_properties(local), "uuid", None)
-    uuid = None if uuid is None else (str(uuid) if str(uuid).startswith("GPU-") else "GPU-" + str(uuid))
-    sampler = ClockSampler(uuid) if rank == 0 else None
     launches0 = ctx.launch_count()
     ctx.set_profiling(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -55,7 +55,8 @@ enum {
 	LIFE_E_NCCL = 3,     /* NCCL error                                           */
 	LIFE_E_STATE = 4,    /* call out of order (e.g. step before upload)          */
 	LIFE_E_SUPPORT = 5,  /* a marker has more than 9 support sites (src/IBMNode.cpp:171-172) */
-	LIFE_E_NOMEM = 6
+	LIFE_E_NOMEM = 6,
+	LIFE_E_IO = 7        /* file could not be opened / read / written (device-fed file paths) */
 };
 
 /* kernel selection for the bulk stream+collide sweep (all produce identical results; bench.py compares them) */
@@ -225,7 +226,53 @@ int life_ibm_set_forces(life_ctx *ctx, const double *force);
 /* Interpolated density / momentum of the last life_ibm_interp (IBMNodeClass::interpRho / interpMom). */
 int life_ibm_get_interp(life_ctx *ctx, double *interp_rho, double *interp_mom);
 
-/* ---- test hooks (bit-exact integer-map checks) ------------------------------------------------------------------------ */
+/* ---- device-fed files ------------------------------------------------------------------------------ */
+/*
+ * The reference writes its fluid files from host arrays, one 8-byte ofstream::write per value (src/Grid.cpp:857-889,
+ * :1192-1221).  These entry points produce the SAME BYTES straight from the device state — an on-device pack kernel lays the
+ * values out in file order (the .vti blocks are j-major, i.e. a transpose of the lattice; the restart records are 120-byte
+ * AoS), double-buffered pinned staging brings them to the host and pwrite() puts them at their final offsets — so the 228 B/node
+ * host mirrors are never needed and, in LIFE_IO_ASYNC mode, the time loop keeps stepping while the file is written
+ * (the state is frozen in a device snapshot first; if that does not fit in HBM the call quietly runs synchronously).
+ * With nranks > 1 every rank writes its own byte ranges of the one shared file.
+ */
+enum { LIFE_IO_SYNC = 0, LIFE_IO_ASYNC = 1 };
+
+/* Everything of Results/VTK/Fluid.<t>.vti that is not array data (src/Grid.cpp:796-855, :891-898): the XML head up to and
+ * including the '_' that opens the raw appended block, and the tail that follows the last array.  Pure host arithmetic, no
+ * device needed.  head/tail may be NULL to query the lengths. */
+int life_vtk_frame(int64_t Nx, int64_t Ny, double Dx, char *head, int64_t head_cap, int64_t *head_len, char *tail,
+                   int64_t tail_cap, int64_t *tail_len);
+
+/* GridClass::writeVTK (src/Grid.cpp:790-898) for the current state: Density = rho*Drho, Pressure = ref_P + (rho - rho_p/Drho)
+ * * SQ(c_s) * Dm / (Dx * SQ(Dt)), Velocity = (u * (Dx/Dt), 0), evaluated in the reference's operation order, written to
+ * `path` byte for byte as the reference's writer would from the same rho / u.  rho_p, ref_P: inc/params.h:51,105. */
+int life_write_vtk(life_ctx *ctx, const char *path, double rho_p, double ref_P, int32_t mode);
+
+/* GridClass::writeRestart (src/Grid.cpp:1163-1229): header (t, Nx, Ny, omega, Dx, Dt, Dm), then per node i, j, rho, u,
+ * force_ibm, f[9]; written to `path`.temp and renamed onto `path` when complete, as the reference does. */
+int life_write_restart(life_ctx *ctx, const char *path, int32_t t, int32_t mode);
+
+/* Completes the pending LIFE_IO_ASYNC write, if any, and returns its status.  Collective when nranks > 1.  Implied by the
+ * next life_write_*, by life_read_restart and by life_destroy. */
+int life_io_wait(life_ctx *ctx);
+
+/* Wall seconds and bytes of the last completed write (this rank's part), and whether it ran asynchronously. */
+int life_io_stats(life_ctx *ctx, double *seconds, int64_t *bytes, int32_t *was_async);
+
+/* Size in bytes of each of the two pinned host / device staging buffers the file paths stream through (default 32 MiB;
+ * tests shrink it to force many chunks). */
+int life_io_set_staging(life_ctx *ctx, int64_t bytes);
+
+/* GridClass::readRestart (src/Grid.cpp:1072-1160) straight into the device state: checks the header against the
+ * configuration and every record's (i, j) against its position, with the reference's own messages on mismatch, and is
+ * otherwise life_upload_state(f, rho, u, force_xy, force_ibm, u_in, rho_in) with the file's contents.  force_xy (2 doubles,
+ * NULL = 0) is the uniform body force initialiseGrid set (src/Grid.cpp:1035-1045; the file does not hold it).
+ * *t_out receives the time step to continue from (GridClass::tOffset).  Each rank reads its own slab. */
+int life_read_restart(life_ctx *ctx, const char *path, const double *force_xy, const double *u_in, const double *rho_in,
+                      int32_t *t_out);
+
+/* ---- test hooks (bit-exact integer-map checks)------------------------------------------------------------------------ */
 
 /* Supports as IBMNodeClass::supp holds them: count [n]; idx, jdx, dirac [n*9] in the reference's i-outer/j-inner order. */
 int life_ibm_get_supports(life_ctx *ctx, int32_t *count, int32_t *idx, int32_t *jdx, double *dirac);

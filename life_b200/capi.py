@@ -16,7 +16,8 @@ ABI_VERSION = 1
 FLUID, WALL, VELOCITY, FREESLIP, PRESSURE, CONVECTIVE = range(6)
 BGK, CENTRAL_MOMENTS = 0, 1
 KERNEL_AUTO, KERNEL_DIRECT, KERNEL_SHUFFLE, KERNEL_TMA = 0, 1, 2, 3
-OK, E_ARG, E_CUDA, E_NCCL, E_STATE, E_SUPPORT, E_NOMEM = range(7)
+OK, E_ARG, E_CUDA, E_NCCL, E_STATE, E_SUPPORT, E_NOMEM, E_IO = range(8)
+IO_SYNC, IO_ASYNC = 0, 1
 
 # every symbol include/life_b200.h declares (tests check the library exports exactly these)
 EXPORTS = [
@@ -27,6 +28,8 @@ EXPORTS = [
     "life_sync", "life_ibm_set_markers", "life_ibm_interp", "life_ibm_spread", "life_ibm_compute_epsilon", "life_ibm_assemble_epsilon", "life_ibm_set_forces",
     "life_ibm_get_interp", "life_ibm_get_supports", "life_get_boundary", "life_get_types", "life_launch_count",
     "life_bulk_kernel_ms", "life_set_profiling",
+    "life_vtk_frame", "life_write_vtk", "life_write_restart", "life_io_wait", "life_io_stats", "life_io_set_staging",
+    "life_read_restart",
 ]
 
 
@@ -113,6 +116,13 @@ def load():
     L.life_launch_count.argtypes = [vp]
     L.life_bulk_kernel_ms.argtypes = [vp, C.POINTER(dbl), C.POINTER(i64)]
     L.life_set_profiling.argtypes = [vp, i32]
+    L.life_vtk_frame.argtypes = [i64, i64, dbl, vp, i64, C.POINTER(i64), vp, i64, C.POINTER(i64)]
+    L.life_write_vtk.argtypes = [vp, C.c_char_p, dbl, dbl, i32]
+    L.life_write_restart.argtypes = [vp, C.c_char_p, i32, i32]
+    L.life_io_wait.argtypes = [vp]
+    L.life_io_stats.argtypes = [vp, C.POINTER(dbl), C.POINTER(i64), C.POINTER(i32)]
+    L.life_io_set_staging.argtypes = [vp, i64]
+    L.life_read_restart.argtypes = [vp, C.c_char_p, vp, vp, vp, C.POINTER(i32)]
     _lib = L
     return L
 
@@ -132,6 +142,20 @@ def slab_range(Nx, nranks, rank):
     if rc:
         raise LifeError(rc, "life_slab_range: bad arguments")
     return b.value, e.value
+
+
+def vtk_frame(Nx, Ny, Dx):
+    """(head, tail) bytes of Fluid.<t>.vti around the raw arrays (life_vtk_frame: pure host arithmetic, no device needed)."""
+    L = load()
+    hl, tl = C.c_int64(), C.c_int64()
+    rc = L.life_vtk_frame(int(Nx), int(Ny), float(Dx), None, 0, C.byref(hl), None, 0, C.byref(tl))
+    if rc:
+        raise LifeError(rc, "life_vtk_frame: bad arguments")
+    head, tail = C.create_string_buffer(hl.value), C.create_string_buffer(tl.value)
+    rc = L.life_vtk_frame(int(Nx), int(Ny), float(Dx), head, hl.value, C.byref(hl), tail, tl.value, C.byref(tl))
+    if rc:
+        raise LifeError(rc, "life_vtk_frame: bad arguments")
+    return head.raw, tail.raw
 
 
 def _ptr(a):
@@ -289,6 +313,31 @@ class Context:
         dirac = np.zeros((n, 9))
         self._ck(self.L.life_ibm_get_supports(self.h, _ptr(count), _ptr(idx), _ptr(jdx), _ptr(dirac)))
         return count, idx, jdx, dirac
+
+    # ---- device-fed files ----
+    def write_vtk(self, path, rho_p, ref_P=0.0, mode=IO_SYNC):
+        self._ck(self.L.life_write_vtk(self.h, os.fsencode(path), float(rho_p), float(ref_P), int(mode)))
+
+    def write_restart(self, path, t, mode=IO_SYNC):
+        self._ck(self.L.life_write_restart(self.h, os.fsencode(path), int(t), int(mode)))
+
+    def io_wait(self):
+        self._ck(self.L.life_io_wait(self.h))
+
+    def io_stats(self):
+        s, b, a = C.c_double(), C.c_int64(), C.c_int32()
+        self._ck(self.L.life_io_stats(self.h, C.byref(s), C.byref(b), C.byref(a)))
+        return s.value, b.value, bool(a.value)
+
+    def io_set_staging(self, nbytes):
+        self._ck(self.L.life_io_set_staging(self.h, int(nbytes)))
+
+    def read_restart(self, path, force_xy=None, u_in=None, rho_in=None):
+        """Returns the time step stored in the file (GridClass::tOffset)."""
+        fxy, u_in, rho_in = _f64(force_xy), _f64(u_in), _f64(rho_in)
+        t = C.c_int32()
+        self._ck(self.L.life_read_restart(self.h, os.fsencode(path), _ptr(fxy), _ptr(u_in), _ptr(rho_in), C.byref(t)))
+        return t.value
 
     # ---- test / measurement hooks ----
     def boundary(self):

@@ -46,6 +46,7 @@ StepScalars step_scalars(life_ctx *ctx, int32_t t) {
 static void free_ctx(life_ctx *ctx) {
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
+	if (ctx->io) { io_wait(ctx); io_free(ctx); }   // completes a pending asynchronous file write first
 	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
 	ibm_free(ctx);
 	if (ctx->comm) ncclCommDestroy(ctx->comm);

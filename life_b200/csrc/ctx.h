@@ -66,6 +66,8 @@ struct MarkerBuffers {
 	bool stage_busy = false;
 };
 
+struct IoState;   // lbm_file.cu
+
 }  // namespace life
 
 struct life_ctx {
@@ -108,6 +110,7 @@ struct life_ctx {
 	int32_t last_t = 0;
 
 	life::MarkerBuffers mk;
+	life::IoState *io = nullptr;          // staging, snapshot and worker of the device-fed file paths (lbm_file.cu)
 	double *scratch = nullptr;            // device staging for upload / download
 	size_t scratch_bytes = 0;
 	double *d_red = nullptr;              // reduction scratch (max speed etc.)
@@ -169,6 +172,10 @@ void ibm_free(life_ctx *ctx);
 // ibm_eps.cu
 int ibm_compute_epsilon(life_ctx *ctx, int64_t nb, const int64_t *first, const int64_t *members, double *eps_out);
 int ibm_assemble_epsilon(life_ctx *ctx, int64_t nb, const int64_t *first, const int64_t *members, double *A_out);
+
+// lbm_file.cu
+int io_wait(life_ctx *ctx);
+void io_free(life_ctx *ctx);
 
 StepScalars step_scalars(life_ctx *ctx, int32_t t);
 

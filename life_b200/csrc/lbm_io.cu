@@ -6,6 +6,7 @@
 //   launch_max_speed              : the scan of GridClass::writeInfo (src/Grid.cpp:562-588)
 #include "ctx.h"
 #include "d2q9.cuh"
+#include "macro.cuh"
 
 namespace life {
 
@@ -119,31 +120,6 @@ int fill_field(life_ctx *ctx, double *planes, int ncomp, int64_t il0, int64_t nc
 }
 
 // ---- end-of-step macroscopics of every node ----------------------------------------------------------------------------------
-struct MacroArgs {
-	const double *f;
-	Layout L;
-	int fxy_mode;
-	double fx, fy;
-	const double *fxyf, *fibm;
-};
-
-__device__ __forceinline__ void node_macro(const MacroArgs &a, int64_t idx, double &rho, double &ux, double &uy) {
-	double p[NV], mx, my;
-#pragma unroll
-	for (int v = 0; v < NV; v++) p[v] = __ldg(a.f + v * a.L.S + idx);
-	moments(p, rho, mx, my);
-	double fx = a.fx, fy = a.fy;
-	if (a.fxy_mode == FXY_FIELD) { fx = a.fxyf[idx]; fy = a.fxyf[a.L.S + idx]; }
-	if (a.fibm) {
-		// (F_xy + F_ibm)/2 as src/IBMNode.cpp:121-122; off-support F_ibm = 0 and this equals src/Grid.cpp:297-298
-		ux = (mx + 0.5 * (fx + a.fibm[idx])) / rho;
-		uy = (my + 0.5 * (fy + a.fibm[a.L.S + idx])) / rho;
-	} else {
-		ux = (mx + 0.5 * fx) / rho;
-		uy = (my + 0.5 * fy) / rho;
-	}
-}
-
 __global__ void __launch_bounds__(256) k_macro(const MacroArgs a, double *out, int64_t c_first) {
 	const int64_t tiles = (a.L.Ny + blockDim.x - 1) / blockDim.x;
 	const int64_t col = c_first + blockIdx.x / tiles;
@@ -157,7 +133,7 @@ __global__ void __launch_bounds__(256) k_macro(const MacroArgs a, double *out, i
 	out[2 * a.L.S + idx] = uy;
 }
 
-static MacroArgs macro_args(life_ctx *ctx) {
+MacroArgs macro_args(life_ctx *ctx) {
 	MacroArgs a{};
 	a.f = ctx->fA;
 	a.L = ctx->L;

@@ -14,8 +14,13 @@
 //                                     =2 -> life_ibm_compute_epsilon (assembly and LU both on the GPU);
 //                                     =3 -> per body: GPU LU for small systems (<= 64 markers, many of them: Honami), GPU
 //                                     assembly + host LAPACK for large ones (UNI_EPSILON: TurekHron 132, PELskin 310)
-//   GridClass::writeInfo / writeVTK / writeRestart (src/Grid.cpp:559, :790, :1163): refresh the host mirrors
-//                                     (life_download_macro / life_download_state), then run the reference's own writer
+//   GridClass::writeInfo / writeVTK / writeRestart / readRestart (src/Grid.cpp:559, :790, :1163, :1072), SURVEY.md §8f row 2:
+//                                     the device-fed file paths — life_max_speed for the scan of writeInfo, life_write_vtk and
+//                                     life_write_restart (asynchronous: the time loop goes on while the file is written) produce
+//                                     the reference's files byte for byte from the device state, life_read_restart streams
+//                                     Fluid.restart straight into it.  The 228 B/node host mirrors are then never refreshed.
+//                                     LIFE_B200_HOST_IO=1 selects the round-trip instead: refresh the host mirrors
+//                                     (life_download_macro / life_download_state), then run the reference's own writer / reader
 //
 // Everything else — main(), params.h / geometry.config, geometryReadIn, the IBMBodyClass constructors, host findSupport /
 // computeDs / computeEpsilon (LAPACK), the corotational FEM + Newmark solve, the Aitken-relaxed sub-iteration loop,
@@ -45,6 +50,7 @@ namespace {
 
 struct DeviceSide {
 	life_ctx *ctx = nullptr;
+	bool uploaded = false;       // the device holds a state (life_upload_state or life_read_restart has run)
 	bool macro_stale = false;    // host rho / u are older than the device state
 	bool full_stale = false;     // host f / force_ibm are older than the device state
 	std::vector<double> pos, vel, ds, eps, force;   // marker staging (SoA)
@@ -125,6 +131,8 @@ life_config make_config(const GridClass &g) {
 void report() {
 	if (!dev.ctx) return;
 	life_sync(dev.ctx);
+	if (life_io_wait(dev.ctx) != LIFE_OK)   // the last asynchronous file write
+		std::fprintf(stderr, "\n[life_b200] file output failed: %s", life_last_error(dev.ctx));
 	const double wall = now() - dev.t_begin;
 	std::fprintf(stderr, "\n[life_b200] wall %.3f s since the first step, of which first step (context + upload) %.3f s; inside life_step %.3f s, "
 	                     "interp %.3f s, spread %.3f s, epsilon %.3f s, download+writers %.3f s; remaining host code %.3f s",
@@ -149,20 +157,36 @@ Fn next_symbol(const char *mangled) {
 
 }  // namespace
 
+namespace {
+
+// LIFE_B200_HOST_IO=1: output / restart through the host mirrors and the reference's own writers instead of the device-fed paths
+bool host_io() {
+	static const bool on = [] { const char *e = std::getenv("LIFE_B200_HOST_IO"); return e && std::atoi(e) != 0; }();
+	return on;
+}
+
+void ensure_context(const GridClass &g) {
+	if (dev.ctx) return;
+	const life_config c = make_config(g);
+	int rc = life_create(&c, &dev.ctx);
+	if (rc != LIFE_OK) {
+		ERROR(std::string("liblife_b200: life_create failed (") + std::to_string(rc) + "): " + life_last_error(nullptr));
+	}
+	std::atexit(report);
+}
+
+}  // namespace
+
 // ---- GridClass::lbmKernel -------------------------------------------------------------------------------------------------------
 void GridClass::lbmKernel() {
-	const bool first = !dev.ctx;
-	if (first) dev.t_begin = now();
+	const bool first = !dev.uploaded;
+	if (dev.t_begin == 0) dev.t_begin = now();
 	Timed timed(first ? dev.t_first : dev.t_step);
-	if (!dev.ctx) {
-		// first step (fresh start or just after readRestart): hand over what initialiseGrid / readRestart produced
-		const life_config c = make_config(*this);
-		int rc = life_create(&c, &dev.ctx);
-		if (rc != LIFE_OK) {
-			ERROR(std::string("liblife_b200: life_create failed (") + std::to_string(rc) + "): " + life_last_error(nullptr));
-		}
+	if (!dev.uploaded) {
+		// first step of a fresh start (or of a restart read on the host): hand over what initialiseGrid / readRestart produced
+		ensure_context(*this);
 		LIFE_CK(life_upload_state(dev.ctx, f.data(), rho.data(), u.data(), force_xy.data(), force_ibm.data(), u_in.data(), rho_in.data()));
-		std::atexit(report);
+		dev.uploaded = true;
 	}
 	LIFE_CK(life_step(dev.ctx, t));
 	dev.steps++;
@@ -189,7 +213,7 @@ void send_markers(std::vector<IBMNodeClass> &iNode) {
 void ObjectsClass::computeEpsilon() {
 	Timed timed(dev.t_eps);
 	static const int on_device = [] { const char *e = std::getenv("LIFE_B200_DEVICE_EPSILON"); return e ? std::atoi(e) : 0; }();
-	if (!on_device || !dev.ctx) {
+	if (!on_device || !dev.uploaded) {
 		// default, and always during construction (t = 0, before the first step creates the context): the reference's own
 		// assembly + LAPACK solve
 		using Fn = void (*)(ObjectsClass *);
@@ -269,36 +293,102 @@ void ObjectsClass::ibmKernelSpread() {
 	dev.macro_stale = dev.full_stale = true;
 }
 
-// ---- output: refresh the host mirrors, then the reference's own writers ------------------------------------------------------------
+// ---- output and restart: device-fed by default, through the host mirrors with LIFE_B200_HOST_IO=1 -------------------------------------
 void GridClass::writeInfo() {
 	Timed timed(dev.t_io);
-	if (dev.ctx && dev.macro_stale) {
-		LIFE_CK(life_download_macro(dev.ctx, rho.data(), u.data()));
-		dev.macro_stale = false;
+	if (!dev.uploaded || host_io()) {
+		if (dev.uploaded && dev.macro_stale) {
+			LIFE_CK(life_download_macro(dev.ctx, rho.data(), u.data()));
+			dev.macro_stale = false;
+		}
+		using Fn = void (*)(GridClass *);
+		static Fn orig = next_symbol<Fn>("_ZN9GridClass9writeInfoEv");
+		orig(this);
+		return;
 	}
-	using Fn = void (*)(GridClass *);
-	static Fn orig = next_symbol<Fn>("_ZN9GridClass9writeInfoEv");
-	orig(this);
+	// the scan of src/Grid.cpp:562-588 on the device, then the same report (src/Grid.cpp:590-616)
+	double vmax = 0.0;
+	int32_t blown = 0;
+	int64_t bi = -1, bj = -1;
+	LIFE_CK(life_max_speed(dev.ctx, &vmax, &blown, &bi, &bj));
+	if (blown) {
+#ifdef VTK
+		Utils::writeVTK(*this);
+		life_io_wait(dev.ctx);
+#endif
+		ERROR("Simulation blew up (t = " + to_string(t) + ") at i = " + to_string(bi) + ", j = " + to_string(bj) + "...exiting");
+	}
+	loopTime = t == tOffset ? 0.0 : (omp_get_wtime() - startTime) / (t - tOffset);
+	const array<int, 3> left = Utils::secs2hms(loopTime * (tOffset + nSteps - t));
+	const double vphys = vmax * Dx / Dt;
+	cout << endl << endl
+	     << "Time step " << t << " of " << tOffset + nSteps << endl
+	     << setprecision(4) << "Simulation has done " << t * Dt << " of " << (tOffset + nSteps) * Dt << " seconds" << endl
+	     << "Time to finish = " << left[0] << " [h] " << left[1] << " [m] " << left[2] << " [s]" << endl
+	     << setprecision(4) << "MLUPS = " << Nx * Ny / (1000000.0 * loopTime) << endl
+	     << setprecision(5) << "Max Velocity = " << vmax << endl
+	     << setprecision(5) << "Max Velocity (m/s) = " << vphys << endl
+	     << setprecision(5) << "Max Reynolds number = " << (vphys)*ref_L / ref_nu;
 }
 
 void GridClass::writeVTK() {
 	Timed timed(dev.t_io);
-	if (dev.ctx && dev.macro_stale) {
-		LIFE_CK(life_download_macro(dev.ctx, rho.data(), u.data()));
-		dev.macro_stale = false;
+	if (!dev.uploaded || host_io() || bigEndian) {
+		if (dev.uploaded && dev.macro_stale) {
+			LIFE_CK(life_download_macro(dev.ctx, rho.data(), u.data()));
+			dev.macro_stale = false;
+		}
+		using Fn = void (*)(GridClass *);
+		static Fn orig = next_symbol<Fn>("_ZN9GridClass8writeVTKEv");
+		orig(this);
+		return;
 	}
-	using Fn = void (*)(GridClass *);
-	static Fn orig = next_symbol<Fn>("_ZN9GridClass8writeVTKEv");
-	orig(this);
+	const string name = "Results/VTK/Fluid." + to_string(t) + ".vti";
+	LIFE_CK(life_write_vtk(dev.ctx, name.c_str(), rho_p, ref_P, LIFE_IO_ASYNC));
+	// placeholders for body files of an earlier run, as src/Grid.cpp:900-912
+	if (!oPtr->hasIBM && boost::filesystem::exists("Results/VTK/IBM.0.vtp")) {
+		string blank = "Results/VTK/IBM." + to_string(t) + ".vtp";
+		oPtr->writeEmptyVTK(blank);
+	}
+#ifdef VTK_FEM
+	if (!oPtr->hasFlex && boost::filesystem::exists("Results/VTK/FEM.0.vtp")) {
+		string blank = "Results/VTK/FEM." + to_string(t) + ".vtp";
+		oPtr->writeEmptyVTK(blank);
+	}
+#endif
 }
 
 void GridClass::writeRestart() {
 	Timed timed(dev.t_io);
-	if (dev.ctx && dev.full_stale) {
-		LIFE_CK(life_download_state(dev.ctx, f.data(), rho.data(), u.data(), force_ibm.data()));
-		dev.full_stale = dev.macro_stale = false;
+	if (!dev.uploaded || host_io() || bigEndian) {
+		if (dev.uploaded && dev.full_stale) {
+			LIFE_CK(life_download_state(dev.ctx, f.data(), rho.data(), u.data(), force_ibm.data()));
+			dev.full_stale = dev.macro_stale = false;
+		}
+		using Fn = void (*)(GridClass *);
+		static Fn orig = next_symbol<Fn>("_ZN9GridClass12writeRestartEv");
+		orig(this);
+		return;
 	}
-	using Fn = void (*)(GridClass *);
-	static Fn orig = next_symbol<Fn>("_ZN9GridClass12writeRestartEv");
-	orig(this);
+	LIFE_CK(life_write_restart(dev.ctx, "Results/Restart/Fluid.restart", t, LIFE_IO_ASYNC));
+}
+
+void GridClass::readRestart() {
+	// force_xy is not in the file; initialiseGrid made it uniform (src/Grid.cpp:1035-1045), which is what the device path takes
+	bool uniform = !force_xy.empty();
+	for (size_t k = 2; k < force_xy.size() && uniform; k += 2) uniform = force_xy[k] == force_xy[0] && force_xy[k + 1] == force_xy[1];
+	if (host_io() || bigEndian || !uniform) {
+		using Fn = void (*)(GridClass *);
+		static Fn orig = next_symbol<Fn>("_ZN9GridClass11readRestartEv");
+		orig(this);
+		return;
+	}
+	ensure_context(*this);
+	int32_t t_file = 0;
+	const int rc = life_read_restart(dev.ctx, "Results/Restart/Fluid.restart", force_xy.data(), u_in.data(), rho_in.data(), &t_file);
+	if (rc != LIFE_OK) ERROR(life_last_error(dev.ctx));   // the reference's own messages (src/Grid.cpp:1080, :1104, :1138)
+	tOffset = t_file;
+	t = tOffset;
+	dev.uploaded = true;
+	dev.macro_stale = dev.full_stale = true;   // the host mirrors keep their initial values and are not read again
 }

@@ -213,3 +213,14 @@ REF_API void ref_refresh_supports(int with_epsilon) {
 
 // Restart files in the reference's own format (Grid.cpp:1163, Objects.cpp:1206) into ./Results/Restart
 REF_API void ref_write_restart() { Utils::writeRestart(*g_grid); }
+
+// Results/VTK/Fluid.<t>.vti by the reference's own writer (Grid.cpp:790-898), whether or not the case defines VTK
+REF_API void ref_write_vtk() { g_grid->writeVTK(); }
+
+// The reference's own reader (Grid.cpp:1072-1160) on ./Results/Restart/Fluid.restart; returns the time step it continued from.
+// A header / index mismatch ends the process through ERROR() (exit 99), as in the reference.
+REF_API int ref_read_restart() {
+	g_grid->readRestart();
+	return g_grid->tOffset;
+}
+REF_API double ref_ref_pressure() { return ref_P; }   // params.h: the constant writeVTK adds to the pressure

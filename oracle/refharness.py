@@ -47,6 +47,7 @@ class RefCase:
         L.ref_create.argtypes = [C.c_char_p]
         L.ref_get_subres.restype = C.c_double
         L.ref_get_relax.restype = C.c_double
+        L.ref_ref_pressure.restype = C.c_double
         # the reference chats on stdout while constructing; silence it at the fd level
         saved = None
         if quiet:
@@ -84,6 +85,7 @@ class RefCase:
         self.ordered = bool(self.flags & self.FLAG_ORDERED)
         self.has_ibm = bool(self.flags & self.FLAG_IBM)
         self.has_flex = bool(self.flags & self.FLAG_FLEX)
+        self.ref_P = float(L.ref_ref_pressure())
 
     # ---- helpers -----------------------------------------------------------------------------------------------
     def _in_workdir(self, fn, *a):
@@ -237,3 +239,13 @@ class RefCase:
     def write_restart(self):
         self._in_workdir(self.lib.ref_write_restart)
         return os.path.join(self.workdir, "Results", "Restart")
+
+    def write_vtk(self):
+        """Results/VTK/Fluid.<t>.vti written by the reference's own GridClass::writeVTK; returns its path."""
+        os.makedirs(os.path.join(self.workdir, "Results", "VTK"), exist_ok=True)   # only made when the case defines VTK
+        self._in_workdir(self.lib.ref_write_vtk)
+        return os.path.join(self.workdir, "Results", "VTK", "Fluid.%d.vti" % self.t)
+
+    def read_restart(self):
+        """GridClass::readRestart on <workdir>/Results/Restart/Fluid.restart; returns tOffset."""
+        return self._in_workdir(self.lib.ref_read_restart)

@@ -55,3 +55,18 @@ def read_table(path):
             continue
     w = max(len(r) for r in rows)
     return np.array([r for r in rows if len(r) == w])
+
+
+def fluid_bytes(t, omega, Dx, Dt, Dm, rho, u, force_ibm, f):
+    """The bytes GridClass::writeRestart (src/Grid.cpp:1163-1221) produces for this state: arrays shaped (Nx, Ny[, k])."""
+    Nx, Ny = rho.shape
+    head = np.zeros(1, _HEAD)
+    head["t"], head["Nx"], head["Ny"] = t, Nx, Ny
+    head["omega"], head["Dx"], head["Dt"], head["Dm"] = omega, Dx, Dt, Dm
+    nodes = np.zeros(Nx * Ny, _NODE)
+    nodes["i"], nodes["j"] = np.divmod(np.arange(Nx * Ny), Ny)
+    nodes["rho"] = np.asarray(rho).reshape(-1)
+    nodes["u"] = np.asarray(u).reshape(-1, 2)
+    nodes["force_ibm"] = np.asarray(force_ibm).reshape(-1, 2)
+    nodes["f"] = np.asarray(f).reshape(-1, 9)
+    return head.tobytes() + nodes.tobytes()

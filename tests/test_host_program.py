@@ -14,6 +14,7 @@ import pytest
 
 from tests import cases as K
 from tests import restartfile as R
+from tests import vtkfile as V
 
 HOST = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "life_b200", "host", "_build")
 EXAMPLES = K.EXAMPLES_LBM + K.EXAMPLES_IBM
@@ -59,21 +60,43 @@ def _compare(case, ref_dir, new_dir):
         tb = R.read_table(os.path.join(new_dir, "Results", "TotalForces.out"))
         assert ta.shape == tb.shape and np.array_equal(ta[:, 0], tb[:, 0])
         err["TotalForces.out"] = float(K.rel_l2(tb[:, 2:4], ta[:, 2:4]))
+    # the last fluid VTK file (written from the device state by life_write_vtk, or by the reference's writer with LIFE_B200_HOST_IO):
+    # same size, same XML head / tail, fields within tolerance
+    va = os.path.join(ref_dir, "Results", "VTK", "Fluid.%d.vti" % a["t"])
+    vb = os.path.join(new_dir, "Results", "VTK", "Fluid.%d.vti" % a["t"])
+    if os.path.exists(va):
+        fa, fb = V.read_fluid(va, a["Nx"], a["Ny"]), V.read_fluid(vb, a["Nx"], a["Ny"])
+        assert os.path.getsize(va) == os.path.getsize(vb)
+        ra, rb = open(va, "rb").read(), open(vb, "rb").read()
+        cut = ra.index(b"_") + 1
+        assert ra[:cut] == rb[:cut] and ra[-40:] == rb[-40:]
+        err["vti density"] = float(K.rel_l2(fb["density"], fa["density"]))
+        # (pressure is an affine map of density that subtracts the mean: its relative error is the density's times |rho| / |rho - rho_0|;
+        #  tests/test_gpu_output.py holds all three blocks to the reference's bytes)
+        err["vti velocity"] = float(K.rel_l2(fb["velocity"], fa["velocity"]))
     return a["t"], err
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("device_eps", [0, 1, 2, 3], ids=["host-eps", "device-assembly+lapack", "device-eps", "auto-eps"])
+@pytest.mark.parametrize("device_eps", [0, 1, 2, 3, "host-io"], ids=["host-eps", "device-assembly+lapack", "device-eps", "auto-eps", "host-io"])
 @pytest.mark.parametrize("case", EXAMPLES)
 def test_program_reproduces_reference_results(case, device_eps, tmp_path):
+    """Default build of the drop-in: device-fed files (life_write_vtk / life_write_restart / life_read_restart / life_max_speed);
+    the "host-io" variant (LIFE_B200_HOST_IO=1) downloads into the host mirrors and runs the reference's own writers."""
     if not (_have(case, "LIFE_b200") and _have(case, "LIFE_ref")):
         pytest.skip("life_b200/host/_build/%s not built (make -C life_b200/host needs /root/reference)" % case)
+    host_io = device_eps == "host-io"
+    if host_io:
+        device_eps = 0
+        if case not in ("ChannelFlow", "TurekHron"):
+            pytest.skip("the host-mirror I/O variant is exercised on one plain and one restarted body case")
     if device_eps and case not in FLEXIBLE:
         pytest.skip("epsilon is only recomputed for flexible bodies")
     times = 2 if case == "TurekHron" else 1          # second run restarts from Results/Restart (store-ref-data.sh:51-53)
     ref = _run(case, "LIFE_ref", str(tmp_path / "ref"), times)
     assert ref.returncode == 0, ref.stdout[-2000:]
-    new = _run(case, "LIFE_b200", str(tmp_path / "b200"), times, LIFE_B200_DEVICE_EPSILON=str(device_eps))
+    new = _run(case, "LIFE_b200", str(tmp_path / "b200"), times, LIFE_B200_DEVICE_EPSILON=str(device_eps),
+               LIFE_B200_HOST_IO="1" if host_io else "0")
     assert new.returncode == 0, new.stdout[-2000:] + new.stderr[-2000:]
     assert "life_step" in new.stderr and " 0 life_step" not in new.stderr      # the CUDA path really ran
     assert (" 0 life_ibm_compute_epsilon" in new.stderr) == (not device_eps)
@@ -81,6 +104,9 @@ def test_program_reproduces_reference_results(case, device_eps, tmp_path):
           % (case, ref.seconds, os.cpu_count(), new.seconds, new.stderr.strip().splitlines()[-1]))
     t_end, err = _compare(case, str(tmp_path / "ref"), str(tmp_path / "b200"))
     assert t_end == 500 * times
+    first = [str(tmp_path / d / "Results" / "VTK" / "Fluid.0.vti") for d in ("ref", "b200")]
+    if all(os.path.exists(x) for x in first):          # the initial state: identical bytes
+        assert open(first[0], "rb").read() == open(first[1], "rb").read()
     assert sorted(os.listdir(tmp_path / "ref" / "Results" / "VTK")) == sorted(os.listdir(tmp_path / "b200" / "Results" / "VTK"))
 
     # TotalForces.out is printed with 10 significant digits (params.h:110)

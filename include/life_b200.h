@@ -257,6 +257,10 @@ int life_write_restart(life_ctx *ctx, const char *path, int32_t t, int32_t mode)
  * next life_write_*, by life_read_restart and by life_destroy. */
 int life_io_wait(life_ctx *ctx);
 
+/* Non-blocking: *busy = 1 while the worker of a LIFE_IO_ASYNC write is still packing / copying / writing (this rank's part),
+ * 0 once life_io_wait would return without waiting for it (or if nothing is pending). */
+int life_io_busy(life_ctx *ctx, int32_t *busy);
+
 /* Wall seconds and bytes of the last completed write (this rank's part), and whether it ran asynchronously. */
 int life_io_stats(life_ctx *ctx, double *seconds, int64_t *bytes, int32_t *was_async);
 

@@ -28,7 +28,7 @@ EXPORTS = [
     "life_sync", "life_ibm_set_markers", "life_ibm_interp", "life_ibm_spread", "life_ibm_compute_epsilon", "life_ibm_assemble_epsilon", "life_ibm_set_forces",
     "life_ibm_get_interp", "life_ibm_get_supports", "life_get_boundary", "life_get_types", "life_launch_count",
     "life_bulk_kernel_ms", "life_set_profiling",
-    "life_vtk_frame", "life_write_vtk", "life_write_restart", "life_io_wait", "life_io_stats", "life_io_set_staging",
+    "life_vtk_frame", "life_write_vtk", "life_write_restart", "life_io_wait", "life_io_busy", "life_io_stats", "life_io_set_staging",
     "life_read_restart",
 ]
 
@@ -120,6 +120,7 @@ def load():
     L.life_write_vtk.argtypes = [vp, C.c_char_p, dbl, dbl, i32]
     L.life_write_restart.argtypes = [vp, C.c_char_p, i32, i32]
     L.life_io_wait.argtypes = [vp]
+    L.life_io_busy.argtypes = [vp, C.POINTER(i32)]
     L.life_io_stats.argtypes = [vp, C.POINTER(dbl), C.POINTER(i64), C.POINTER(i32)]
     L.life_io_set_staging.argtypes = [vp, i64]
     L.life_read_restart.argtypes = [vp, C.c_char_p, vp, vp, vp, C.POINTER(i32)]
@@ -323,6 +324,11 @@ class Context:
 
     def io_wait(self):
         self._ck(self.L.life_io_wait(self.h))
+
+    def io_busy(self):
+        b = C.c_int32()
+        self._ck(self.L.life_io_busy(self.h, C.byref(b)))
+        return bool(b.value)
 
     def io_stats(self):
         s, b, a = C.c_double(), C.c_int64(), C.c_int32()

@@ -21,6 +21,7 @@
 #include "d2q9.cuh"
 #include "macro.cuh"
 #include <algorithm>
+#include <atomic>
 #include <cerrno>
 #include <chrono>
 #include <cmath>
@@ -255,6 +256,7 @@ struct IoState {
 	size_t snap_bytes = 0;
 	std::thread worker;
 	bool pending = false;                        // a job has been started and not yet completed by io_wait
+	std::atomic<bool> finished{true};            // the thread running the job has written its result fields
 	FileJob job;
 	// result of the job (written by the thread that runs it, read after the join)
 	int rc = LIFE_OK;
@@ -268,7 +270,13 @@ namespace {
 
 // Runs on the caller's thread (synchronous) or on the worker (asynchronous).  Touches only the job, the staging buffers and the
 // result fields of IoState.
+void run_job_body(IoState *io);
 void run_job(IoState *io) {
+	run_job_body(io);
+	io->finished.store(true, std::memory_order_release);
+}
+
+void run_job_body(IoState *io) {
 	const FileJob &job = io->job;
 	const double t_begin = now_s();
 	io->rc = LIFE_OK;
@@ -498,6 +506,7 @@ int start_job(life_ctx *ctx, FileJob &job, int mode) {
 	io->job = job;
 	io->was_async = async;
 	io->pending = true;
+	io->finished.store(false, std::memory_order_relaxed);
 	if (async) {
 		io->worker = std::thread(run_job, io);
 		return LIFE_OK;
@@ -508,6 +517,15 @@ int start_job(life_ctx *ctx, FileJob &job, int mode) {
 
 }  // namespace
 
+// all ranks have reached this point (a one-element all-reduce on the compute stream, then a host wait)
+static int comm_barrier(life_ctx *ctx) {
+	if (!ctx->d_red) LIFE_CUDA(ctx, cudaMalloc(&ctx->d_red, 64));
+	LIFE_CUDA(ctx, cudaMemsetAsync(ctx->d_red + 4, 0, sizeof(double), ctx->stream));
+	LIFE_NCCL(ctx, ncclAllReduce(ctx->d_red + 4, ctx->d_red + 4, 1, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+	LIFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return LIFE_OK;
+}
+
 int io_wait(life_ctx *ctx) {
 	IoState *io = ctx->io;
 	if (!io || !io->pending) return LIFE_OK;
@@ -517,16 +535,16 @@ int io_wait(life_ctx *ctx) {
 	int rc = io->rc;
 	std::string err = io->err;
 	if (ctx->comm) {
-		// every rank's bytes must be in the file before rank 0 renames it / before anyone reads it back
-		if (!ctx->d_red) LIFE_CUDA(ctx, cudaMalloc(&ctx->d_red, 64));
-		LIFE_CUDA(ctx, cudaMemsetAsync(ctx->d_red + 4, 0, sizeof(double), ctx->stream));
-		LIFE_NCCL(ctx, ncclAllReduce(ctx->d_red + 4, ctx->d_red + 4, 1, ncclDouble, ncclSum, ctx->comm, ctx->stream));
-		LIFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		// every rank's bytes must be in the file before rank 0 renames it, and the rename must have happened before any rank
+		// goes on (to read the file back, or to open the next .temp)
+		int brc = comm_barrier(ctx);
+		if (brc) return brc;
 		if (rc == LIFE_OK && io->job.kind == JOB_RESTART && ctx->cfg.rank == 0 &&
 		    rename(io->job.path.c_str(), io->job.final_path.c_str()) != 0) {
 			rc = LIFE_E_IO;
 			err = "rename " + io->job.path + ": " + strerror(errno);
 		}
+		if ((brc = comm_barrier(ctx))) return brc;
 	}
 	if (rc) return fail(ctx, rc, err);
 	return LIFE_OK;
@@ -613,6 +631,13 @@ int life_io_wait(life_ctx *ctx) {
 	if (!ctx) return LIFE_E_ARG;
 	LIFE_CUDA(ctx, cudaSetDevice(ctx->device));
 	return io_wait(ctx);
+}
+
+int life_io_busy(life_ctx *ctx, int32_t *busy) {
+	if (!ctx || !busy) return LIFE_E_ARG;
+	const IoState *io = ctx->io;
+	*busy = io && io->pending && !io->finished.load(std::memory_order_acquire) ? 1 : 0;
+	return LIFE_OK;
 }
 
 int life_io_stats(life_ctx *ctx, double *seconds, int64_t *bytes, int32_t *was_async) {

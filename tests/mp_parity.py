@@ -5,6 +5,9 @@
 Every rank builds the oracle's whole-lattice state (deterministic), takes its x-slab, steps it through the C ABI with the
 NCCL halo exchange, and compares its slab with the oracle's whole-lattice result: fields and marker forces within relative
 L2 1e-10.  For cases with bodies the recorded call-site trace of the compiled reference (tests/golden) drives the markers.
+With a fourth argument (a directory visible to every rank) the ranks also write ONE Fluid.<t>.vti and ONE Fluid.restart
+together (life_write_vtk / life_write_restart: every rank its own byte ranges), rank 0 checks the bytes against the reference
+format built from the gathered slabs, and every rank reads its slab back with life_read_restart.
 Exit code 0 = parity on every rank.
 """
 import os
@@ -29,7 +32,7 @@ def main():
     nid = D.share_nccl_id()
 
     g = K.golden(case)
-    steps = int(sys.argv[2]) if len(sys.argv) > 2 else int(g["steps"])
+    steps = (int(sys.argv[2]) if len(sys.argv) > 2 else 0) or int(g["steps"])
     o = K.make_oracle(g)
     cfg = K.life_config(o.params, o, rank=rank, nranks=world, device=local)
     ctx = capi.Context(cfg, nccl_id=nid)
@@ -68,10 +71,38 @@ def main():
         o.step(steps)
     vmax, has_nan, _, _ = ctx.max_speed()
     st = ctx.download_state()
-    ctx.close()
 
     ok = True
     msgs = []
+    if len(sys.argv) > 3:
+        from tests import restartfile as R, vtkfile as V
+        out = sys.argv[3]
+        vti, rst = os.path.join(out, "Fluid.%d.vti" % steps), os.path.join(out, "Fluid.restart")
+        slabs = [None] * world
+        dist.all_gather_object(slabs, st)
+        for mode in (capi.IO_SYNC, capi.IO_ASYNC):
+            ctx.write_vtk(vti, o.params.rho_p, 0.5, mode)
+            ctx.write_restart(rst, steps, mode)
+            ctx.io_wait()                      # collective: all bytes are in the files, rank 0 has renamed the restart file
+            if rank == 0:
+                whole = {k: np.concatenate([s_[k] for s_ in slabs], axis=0) for k in st}
+                want_vti = V.fluid_bytes(whole["rho"], whole["u"], o.Dx, o.Dt, o.Dm, o.Drho, o.params.rho_p, 0.5)
+                want_rst = R.fluid_bytes(steps, o.params.omega, o.Dx, o.Dt, o.Dm, whole["rho"], whole["u"], whole["force_ibm"], whole["f"])
+                if open(vti, "rb").read() != want_vti:
+                    ok = False
+                    msgs.append("shared .vti differs (mode %d)" % mode)
+                if open(rst, "rb").read() != want_rst or os.path.exists(rst + ".temp"):
+                    ok = False
+                    msgs.append("shared Fluid.restart differs (mode %d)" % mode)
+            dist.barrier()
+        back = capi.Context(K.life_config(o.params, o, rank=rank, nranks=world, device=local), nccl_id=D.share_nccl_id())
+        t_file = back.read_restart(rst, o.get("force_xy").reshape(-1, 2)[0], o.get("u_in"), o.get("rho_in"))
+        sb = back.download_state()
+        back.close()
+        if t_file != steps or any(not np.array_equal(sb[k], st[k]) for k in st):
+            ok = False
+            msgs.append("life_read_restart did not return this rank's slab")
+    ctx.close()
     if has_ibm:
         if not worst_force < K.TOL:
             ok = False

@@ -106,7 +106,7 @@ def test_async_write_freezes_the_state_while_the_steps_go_on(case, tmp_path):
     st2 = ctx.download_state()
     t = _advance(case, ctx, t, 5)
     ctx.io_wait()
-    assert ctx.io_stats()[2] is True
+    assert ctx.io_stats()[2] is True and not ctx.io_busy()
     want_vti2, _ = _expected(o, st2, t)
     assert open(tmp_path / "a.vti", "rb").read() == want_vti2
     assert not np.array_equal(st["f"], st2["f"])

@@ -222,6 +222,7 @@ int life_upload_begin(life_ctx *ctx, const double *u_in, const double *rho_in) {
 	ctx->fibm_any = false;
 	ctx->fibm_sites_dirty = false;
 	ctx->fibm_full_dirty = false;
+	ctx->fibm_consumed = true;
 	if (ctx->fibm) LIFE_CUDA(ctx, cudaMemsetAsync(ctx->fibm, 0, sizeof(double) * 2 * L.S, ctx->stream));
 	if (ctx->wom_field) {   // force_xy is a field the sweep recomputes every step (src/Grid.cpp:55-61)
 		if (!ctx->fxyf) LIFE_CUDA(ctx, cudaMalloc(&ctx->fxyf, sizeof(double) * 2 * L.S));
@@ -303,6 +304,7 @@ int life_upload_columns(life_ctx *ctx, int64_t il0, int64_t ncols, const double 
 			if ((rc = upload_field(ctx, force_ibm, ctx->fibm, 2, il0, ncols))) return rc;
 			ctx->fibm_any = true;
 			ctx->fibm_full_dirty = true;
+			ctx->fibm_consumed = false;
 		}
 	}
 	// the host arrays belong to the caller: do not return before the copies out of them have completed
@@ -439,6 +441,7 @@ int life_step(life_ctx *ctx, int32_t t) {
 
 	double *tmp = ctx->fA; ctx->fA = ctx->fB; ctx->fB = tmp;
 	ctx->stored_macro_valid = false;
+	ctx->fibm_consumed = true;
 	ctx->fxy_uniform[0] = sc.fxy_cur[0];
 	ctx->fxy_uniform[1] = sc.fxy_cur[1];
 	ctx->last_t = t;

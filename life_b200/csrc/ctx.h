@@ -107,6 +107,7 @@ struct life_ctx {
 	bool fibm_any = false;                // force_ibm may be non-zero somewhere
 	bool fibm_sites_dirty = false;        // non-zero only at the current support sites
 	bool fibm_full_dirty = false;         // non-zero anywhere (uploaded)
+	bool fibm_consumed = true;            // a life_step has used the current force_ibm (it may be cleared when the markers move)
 	int32_t last_t = 0;
 
 	life::MarkerBuffers mk;

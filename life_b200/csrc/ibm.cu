@@ -156,8 +156,14 @@ int ibm_clear_force(life_ctx *ctx) {
 
 int ibm_set_markers(life_ctx *ctx, int64_t n, const double *pos, const double *vel, const double *ds, const double *eps) {
 	int rc;
-	// force_ibm is non-zero at the OLD supports: clear it before they are replaced
-	if ((rc = ibm_clear_force(ctx))) return rc;
+	// force_ibm is non-zero at the OLD supports: clear it before they are replaced — unless no step has used it yet (markers
+	// set between a spread, an upload or life_read_restart and the next life_step: the reference keeps force_ibm until
+	// ibmKernelInterp zeroes it, src/Objects.cpp:105); then it stays and is cleared wholesale later
+	if (ctx->fibm_consumed) {
+		if ((rc = ibm_clear_force(ctx))) return rc;
+	} else if (ctx->fibm_sites_dirty) {
+		ctx->fibm_full_dirty = true;
+	}
 	if ((rc = ensure_markers(ctx, n))) return rc;
 	MarkerBuffers &m = ctx->mk;
 	m.n = n;
@@ -451,6 +457,7 @@ int ibm_spread(life_ctx *ctx) {
 	LIFE_CUDA(ctx, cudaGetLastError());
 	ctx->fibm_any = true;
 	ctx->fibm_sites_dirty = true;
+	ctx->fibm_consumed = false;
 	return LIFE_OK;
 }
 

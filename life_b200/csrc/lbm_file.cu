@@ -747,6 +747,7 @@ int life_read_restart(life_ctx *ctx, const char *path, const double *force_xy, c
 	if (any_fibm) {
 		ctx->fibm_any = true;
 		ctx->fibm_full_dirty = true;
+		ctx->fibm_consumed = false;
 	}
 	if ((rc = life_upload_end(ctx))) return rc;
 	if (t_out) *t_out = hi[0];

@@ -313,3 +313,23 @@ def test_mid_size_lattice_default_staging(mode, tmp_path):
             assert np.array_equal(back[name], sb[name]), name
         b.close()
     ctx.close()
+
+
+def test_markers_sent_before_the_next_step_do_not_drop_the_spread_force():
+    """The reference keeps force_ibm from ibmKernelSpread until the next ibmKernelInterp zeroes it (src/Objects.cpp:105): sending
+    the markers again in between (what the host does when it recomputes epsilon right after a restart, src/Objects.cpp:1184-1185)
+    must not clear the force the next lbmKernel is about to use."""
+    g, o, a = _start("Cylinder")
+    _, _, b = _start("Cylinder")
+    for t in range(1, 9):
+        for ctx in (a, b):
+            ctx.step(t)
+            ctx.ibm_interp()
+            ctx.ibm_spread()
+        b.ibm_set_markers(g["m_pos"], g["m_vel"], g["m_ds"], g["m_eps"])       # between spread and the next step
+    sa, sb = a.download_state(), b.download_state()
+    assert np.abs(sa["force_ibm"]).max() > 0
+    for name in ("f", "rho", "u", "force_ibm"):
+        assert np.array_equal(sa[name], sb[name]), name
+    a.close()
+    b.close()

@@ -220,6 +220,73 @@ bool read_at(int fd, void *buf, size_t n, int64_t off, std::string &err) {
 	return true;
 }
 
+// One contiguous run of a chunk <-> the file, split over a few host threads: the copy between the pinned buffer and the page
+// cache (and, for a fresh file, the page and block allocation behind it) is what bounds these paths, and it scales with cores.
+int io_threads() {
+	static const int n = [] {
+		const unsigned hc = std::thread::hardware_concurrency();
+		return (int)std::max(1u, std::min(8u, hc / 2));
+	}();
+	return n;
+}
+
+template <bool WRITE>
+bool transfer_at(int fd, char *buf, size_t n, int64_t off, std::string &err) {
+	constexpr size_t MIN_PIECE = (size_t)4 << 20;
+	const int parts = (int)std::max<size_t>(1, std::min<size_t>((size_t)io_threads(), n / MIN_PIECE));
+	if (parts == 1) return WRITE ? write_at(fd, buf, n, off, err) : read_at(fd, buf, n, off, err);
+	const size_t piece = ((n / parts) + 4095) & ~(size_t)4095;
+	std::vector<std::string> errs((size_t)parts);
+	std::vector<char> okv((size_t)parts, 1);
+	std::vector<std::thread> th;
+	auto work = [&](int k) {
+		const size_t b = (size_t)k * piece, e = std::min(n, b + piece);
+		if (b >= e) return;
+		okv[(size_t)k] = (WRITE ? write_at(fd, buf + b, e - b, off + (int64_t)b, errs[(size_t)k]) : read_at(fd, buf + b, e - b, off + (int64_t)b, errs[(size_t)k])) ? 1 : 0;
+	};
+	for (int k = 1; k < parts; k++) th.emplace_back(work, k);
+	work(0);
+	for (auto &t : th) t.join();
+	for (int k = 0; k < parts; k++)
+		if (!okv[(size_t)k]) { err = errs[(size_t)k]; return false; }
+	return true;
+}
+
+// Restart records of `ncols` whole columns starting at global column i0: false if a record does not carry its own (i, j);
+// any_force = some record holds a non-zero force_ibm.  Columns are split over the host threads.
+bool scan_records(const char *h, int64_t ncols, int64_t Ny, int64_t i0, bool &any_force) {
+	const int parts = (int)std::max<int64_t>(1, std::min<int64_t>(io_threads(), ncols * Ny / 65536));
+	std::vector<char> good((size_t)parts, 1), force((size_t)parts, 0);
+	auto work = [&](int k) {
+		const int64_t cb = ncols * k / parts, ce = ncols * (k + 1) / parts;
+		bool g = true, f = false;
+		for (int64_t c = cb; c < ce && g; c++) {
+			const char *rec = h + c * Ny * 8 * RW;
+			const int32_t i = (int32_t)(i0 + c);
+			for (int64_t j = 0; j < Ny; j++, rec += 8 * RW) {
+				int32_t ij[2];
+				double fxy[2];
+				memcpy(ij, rec, 8);
+				memcpy(fxy, rec + 32, 16);
+				if (ij[0] != i || ij[1] != (int32_t)j) { g = false; break; }
+				f = f || fxy[0] != 0.0 || fxy[1] != 0.0;
+			}
+		}
+		good[(size_t)k] = g;
+		force[(size_t)k] = f;
+	};
+	std::vector<std::thread> th;
+	for (int k = 1; k < parts; k++) th.emplace_back(work, k);
+	work(0);
+	for (auto &t : th) t.join();
+	any_force = false;
+	for (int k = 0; k < parts; k++) {
+		if (!good[(size_t)k]) return false;
+		any_force = any_force || force[(size_t)k];
+	}
+	return true;
+}
+
 struct FileJob {
 	int kind = JOB_VTK;
 	std::string path;                 // where the bytes go (restart: the .temp name)
@@ -364,14 +431,14 @@ void run_job_body(IoState *io) {
 	auto flush = [&](const Chunk &c, int s) -> bool {
 		const cudaError_t e = cudaEventSynchronize(io->ev_slot[s]);
 		if (e != cudaSuccess) { cuda_fail("file chunk", e); return false; }
-		const char *h = static_cast<const char *>(io->h_stage[s]);
+		char *h = static_cast<char *>(io->h_stage[s]);
 		bool w = true;
 		if (job.kind == JOB_RESTART) {
-			w = write_at(fd, h, chunk_bytes(c), RESTART_HEAD + ((job.i_begin + c.a0) * Ny) * 8 * RW, io->err);
+			w = transfer_at<true>(fd, h, chunk_bytes(c), RESTART_HEAD + ((job.i_begin + c.a0) * Ny) * 8 * RW, io->err);
 		} else {
 			const int64_t comp8 = 8 * (c.block == 2 ? 3 : 1);
 			if (nxl == Nx) {   // whole rows: one contiguous run
-				w = write_at(fd, h, chunk_bytes(c), data_off[c.block] + c.a0 * Nx * comp8, io->err);
+				w = transfer_at<true>(fd, h, chunk_bytes(c), data_off[c.block] + c.a0 * Nx * comp8, io->err);
 			} else {           // this slab's segment of every row
 				for (int64_t r = 0; r < c.an && w; r++)
 					w = write_at(fd, h + r * nxl * comp8, (size_t)(nxl * comp8), data_off[c.block] + ((c.a0 + r) * Nx + job.i_begin) * comp8, io->err);
@@ -707,23 +774,15 @@ int life_read_restart(life_ctx *ctx, const char *path, const double *force_xy, c
 		const size_t bytes = (size_t)(nc * col_bytes);
 		if (k >= 2) LIFE_CUDA(ctx, cudaEventSynchronize(io->ev_slot[s]));   // the copy out of this slot two chunks ago
 		char *h = static_cast<char *>(io->h_stage[s]);
-		if (!read_at(fd, h, bytes, RESTART_HEAD + (ctx->i_begin + c0) * col_bytes, err)) {
+		if (!transfer_at<false>(fd, h, bytes, RESTART_HEAD + (ctx->i_begin + c0) * col_bytes, err)) {
 			cudaStreamSynchronize(ctx->stream);
 			return fail(ctx, LIFE_E_IO, "life_read_restart: " + err);
 		}
 		// src/Grid.cpp:1137-1138: every record must sit at its own (i, j); and is there any IBM force at all?
 		bool chunk_fibm = false;
-		for (int64_t n = 0; n < nc * L.Ny; n++) {
-			const char *rec = h + n * 8 * RW;
-			int32_t ij[2];
-			double fxy[2];
-			memcpy(ij, rec, 8);
-			memcpy(fxy, rec + 32, 16);
-			if (ij[0] != (int32_t)(ctx->i_begin + c0 + n / L.Ny) || ij[1] != (int32_t)(n % L.Ny)) {
-				cudaStreamSynchronize(ctx->stream);
-				return fail(ctx, LIFE_E_ARG, "Grid indices do not match Fluid.restart file...exiting");
-			}
-			chunk_fibm = chunk_fibm || fxy[0] != 0.0 || fxy[1] != 0.0;
+		if (!scan_records(h, nc, L.Ny, ctx->i_begin + c0, chunk_fibm)) {
+			cudaStreamSynchronize(ctx->stream);
+			return fail(ctx, LIFE_E_ARG, "Grid indices do not match Fluid.restart file...exiting");
 		}
 		if (chunk_fibm && !any_fibm) {
 			if ((rc = ensure_fibm(ctx))) return rc;   // zero-filled: the chunks before this one held no force

@@ -485,7 +485,7 @@ int ensure_io(life_ctx *ctx) {
 // two device + two pinned staging buffers, each able to hold at least one .vti velocity row and one restart column
 int ensure_staging(life_ctx *ctx) {
 	IoState *io = ctx->io;
-	size_t need = io->want_bytes;
+	size_t need = std::min(io->want_bytes, (size_t)(ctx->L.nxl * ctx->L.Ny * 8 * RW));   // never more than this slab's restart records
 	need = std::max(need, (size_t)(ctx->L.nxl * 24));
 	need = std::max(need, (size_t)(ctx->L.Ny * 8 * RW));
 	need = (need + 255) & ~(size_t)255;

@@ -59,6 +59,7 @@ struct DeviceSide {
 	std::vector<double> eps_mat;
 	// wall-clock accounting (seconds spent inside each replaced body; the rest of the program is the reference's host code)
 	double t_step = 0, t_interp = 0, t_spread = 0, t_eps = 0, t_io = 0, t_first = 0, t_begin = 0;
+	double t_info = 0, t_vtk = 0, t_restart = 0;   // parts of t_io
 } dev;
 
 double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -135,8 +136,9 @@ void report() {
 		std::fprintf(stderr, "\n[life_b200] file output failed: %s", life_last_error(dev.ctx));
 	const double wall = now() - dev.t_begin;
 	std::fprintf(stderr, "\n[life_b200] wall %.3f s since the device context was created, of which context + first upload / restart read %.3f s; "
-	                     "inside life_step %.3f s, interp %.3f s, spread %.3f s, epsilon %.3f s, output calls %.3f s; remaining host code %.3f s",
-	             wall, dev.t_first, dev.t_step, dev.t_interp, dev.t_spread, dev.t_eps, dev.t_io,
+	                     "inside life_step %.3f s, interp %.3f s, spread %.3f s, epsilon %.3f s, output calls %.3f s (writeInfo %.3f, writeVTK %.3f, "
+	                     "writeRestart %.3f); remaining host code %.3f s",
+	             wall, dev.t_first, dev.t_step, dev.t_interp, dev.t_spread, dev.t_eps, dev.t_io, dev.t_info, dev.t_vtk, dev.t_restart,
 	             wall - dev.t_first - dev.t_step - dev.t_interp - dev.t_spread - dev.t_eps - dev.t_io);
 	if (dev.steps > 1)
 		std::fprintf(stderr, "\n[life_b200] steady state %.1f us per time step = %.1f MLUPS (%ld x %ld lattice, %ld steps, all host work and output included)",
@@ -302,7 +304,7 @@ void ObjectsClass::ibmKernelSpread() {
 // ---- output and restart: device-fed by default, through the host mirrors with LIFE_B200_HOST_IO=1 -------------------------------------
 void GridClass::writeInfo() {
 	if (!host_io()) ensure_state(*this);
-	Timed timed(dev.t_io);
+	Timed timed(dev.t_io), part(dev.t_info);
 	if (host_io()) {
 		if (dev.uploaded && dev.macro_stale) {
 			LIFE_CK(life_download_macro(dev.ctx, rho.data(), u.data()));
@@ -340,7 +342,7 @@ void GridClass::writeInfo() {
 
 void GridClass::writeVTK() {
 	if (!(host_io() || bigEndian)) ensure_state(*this);
-	Timed timed(dev.t_io);
+	Timed timed(dev.t_io), part(dev.t_vtk);
 	if (host_io() || bigEndian) {
 		if (dev.uploaded && dev.macro_stale) {
 			LIFE_CK(life_download_macro(dev.ctx, rho.data(), u.data()));
@@ -368,7 +370,7 @@ void GridClass::writeVTK() {
 
 void GridClass::writeRestart() {
 	if (!(host_io() || bigEndian)) ensure_state(*this);
-	Timed timed(dev.t_io);
+	Timed timed(dev.t_io), part(dev.t_restart);
 	if (host_io() || bigEndian) {
 		if (dev.uploaded && dev.full_stale) {
 			LIFE_CK(life_download_state(dev.ctx, f.data(), rho.data(), u.data(), force_ibm.data()));

@@ -30,6 +30,7 @@
 #include <sstream>
 #include <sys/stat.h>
 #include <sys/types.h>
+#include <system_error>
 #include <thread>
 #include <unistd.h>
 
@@ -244,7 +245,10 @@ bool transfer_at(int fd, char *buf, size_t n, int64_t off, std::string &err) {
 		if (b >= e) return;
 		okv[(size_t)k] = (WRITE ? write_at(fd, buf + b, e - b, off + (int64_t)b, errs[(size_t)k]) : read_at(fd, buf + b, e - b, off + (int64_t)b, errs[(size_t)k])) ? 1 : 0;
 	};
-	for (int k = 1; k < parts; k++) th.emplace_back(work, k);
+	for (int k = 1; k < parts; k++) {
+		try { th.emplace_back(work, k); }
+		catch (const std::system_error &) { work(k); }   // no thread to be had: do that piece here
+	}
 	work(0);
 	for (auto &t : th) t.join();
 	for (int k = 0; k < parts; k++)
@@ -276,7 +280,10 @@ bool scan_records(const char *h, int64_t ncols, int64_t Ny, int64_t i0, bool &an
 		force[(size_t)k] = f;
 	};
 	std::vector<std::thread> th;
-	for (int k = 1; k < parts; k++) th.emplace_back(work, k);
+	for (int k = 1; k < parts; k++) {
+		try { th.emplace_back(work, k); }
+		catch (const std::system_error &) { work(k); }
+	}
 	work(0);
 	for (auto &t : th) t.join();
 	any_force = false;
@@ -575,8 +582,12 @@ int start_job(life_ctx *ctx, FileJob &job, int mode) {
 	io->pending = true;
 	io->finished.store(false, std::memory_order_relaxed);
 	if (async) {
-		io->worker = std::thread(run_job, io);
-		return LIFE_OK;
+		try {
+			io->worker = std::thread(run_job, io);
+			return LIFE_OK;
+		} catch (const std::system_error &) {
+			// no worker thread to be had: the job (already pointed at the snapshot and the side stream) runs here instead
+		}
 	}
 	run_job(io);
 	return io_wait(ctx);

@@ -104,6 +104,15 @@ def test_program_reproduces_reference_results(case, device_eps, tmp_path):
           % (case, ref.seconds, os.cpu_count(), new.seconds, new.stderr.strip().splitlines()[-1]))
     t_end, err = _compare(case, str(tmp_path / "ref"), str(tmp_path / "b200"))
     assert t_end == 500 * times
+    # the report of writeInfo (src/Grid.cpp:590-616; from life_max_speed in the drop-in): same lines, same numbers as printed
+    info = lambda out, pat: re.findall(pat, out)
+    for pat in (r"Time step (\d+) of (\d+)", r"Simulation has done (\S+) of (\S+) seconds"):
+        assert info(new.stdout, pat) == info(ref.stdout, pat) and len(info(ref.stdout, pat)) == 51, pat
+    for pat in (r"Max Velocity = (\S+)", r"Max Velocity \(m/s\) = (\S+)", r"Max Reynolds number = (\S+)"):
+        a, b = np.array(info(ref.stdout, pat), float), np.array(info(new.stdout, pat), float)
+        assert a.shape == b.shape == (51,), pat
+        if case not in FLEXIBLE:     # (flexible bodies: the fields themselves only agree to the reference's self-difference, see below)
+            assert np.allclose(b, a, rtol=2e-4, atol=1e-12), (pat, a, b)
     first = [str(tmp_path / d / "Results" / "VTK" / "Fluid.0.vti") for d in ("ref", "b200")]
     if all(os.path.exists(x) for x in first):          # the initial state: identical bytes
         assert open(first[0], "rb").read() == open(first[1], "rb").read()

@@ -9,25 +9,8 @@ Little endian, native int / size_t / double, written field by field (no padding)
 """
 import numpy as np
 
-_HEAD = np.dtype([("t", "<i4"), ("Nx", "<i4"), ("Ny", "<i4"), ("omega", "<f8"), ("Dx", "<f8"), ("Dt", "<f8"), ("Dm", "<f8")])
-_NODE = np.dtype([("i", "<i4"), ("j", "<i4"), ("rho", "<f8"), ("u", "<f8", (2,)), ("force_ibm", "<f8", (2,)), ("f", "<f8", (9,))])
-assert _HEAD.itemsize == 44 and _NODE.itemsize == 120
-
-
-def read_fluid(path):
-    raw = np.fromfile(path, dtype=np.uint8)
-    head = raw[:44].view(_HEAD)[0]
-    Nx, Ny = int(head["Nx"]), int(head["Ny"])
-    assert raw.size == 44 + 120 * Nx * Ny, (raw.size, Nx, Ny)
-    nodes = raw[44:].view(_NODE)
-    ii, jj = np.divmod(np.arange(Nx * Ny), Ny)
-    assert np.array_equal(nodes["i"], ii) and np.array_equal(nodes["j"], jj)
-    out = {k: head[k].item() for k in _HEAD.names}
-    out["rho"] = nodes["rho"].reshape(Nx, Ny).copy()
-    out["u"] = nodes["u"].reshape(Nx, Ny, 2).copy()
-    out["force_ibm"] = nodes["force_ibm"].reshape(Nx, Ny, 2).copy()
-    out["f"] = nodes["f"].reshape(Nx, Ny, 9).copy()
-    return out
+from oracle.fluidfiles import read_restart as read_fluid  # noqa: F401  (format restatement: oracle/fluidfiles.py)
+from oracle.fluidfiles import restart_bytes as fluid_bytes  # noqa: F401
 
 
 def read_ibm(path):
@@ -55,18 +38,3 @@ def read_table(path):
             continue
     w = max(len(r) for r in rows)
     return np.array([r for r in rows if len(r) == w])
-
-
-def fluid_bytes(t, omega, Dx, Dt, Dm, rho, u, force_ibm, f):
-    """The bytes GridClass::writeRestart (src/Grid.cpp:1163-1221) produces for this state: arrays shaped (Nx, Ny[, k])."""
-    Nx, Ny = rho.shape
-    head = np.zeros(1, _HEAD)
-    head["t"], head["Nx"], head["Ny"] = t, Nx, Ny
-    head["omega"], head["Dx"], head["Dt"], head["Dm"] = omega, Dx, Dt, Dm
-    nodes = np.zeros(Nx * Ny, _NODE)
-    nodes["i"], nodes["j"] = np.divmod(np.arange(Nx * Ny), Ny)
-    nodes["rho"] = np.asarray(rho).reshape(-1)
-    nodes["u"] = np.asarray(u).reshape(-1, 2)
-    nodes["force_ibm"] = np.asarray(force_ibm).reshape(-1, 2)
-    nodes["f"] = np.asarray(f).reshape(-1, 9)
-    return head.tobytes() + nodes.tobytes()

@@ -82,3 +82,19 @@ def test_product_does_not_touch_the_oracle():
                 if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp", ".c")):
                     txt = open(os.path.join(dp, fn), errors="ignore").read()
                     assert "oracle" not in txt.lower() or fn == "capi.py" and False, os.path.join(dp, fn)
+
+
+def test_file_entry_points_reject_bad_arguments_without_a_device(lib_built):
+    """The device-fed file entry points validate their arguments before touching CUDA (no context can exist on this machine)."""
+    import ctypes as C
+    from life_b200 import capi
+    L = capi.load()
+    assert L.life_write_vtk(None, b"/tmp/x.vti", 1.0, 0.0, capi.IO_SYNC) == capi.E_ARG
+    assert L.life_write_restart(None, b"/tmp/x.restart", 1, capi.IO_ASYNC) == capi.E_ARG
+    assert L.life_read_restart(None, b"/tmp/x.restart", None, None, None, None) == capi.E_ARG
+    assert L.life_io_wait(None) == capi.E_ARG
+    assert L.life_io_set_staging(None, 1 << 20) == capi.E_ARG
+    busy = C.c_int32(7)
+    assert L.life_io_busy(None, C.byref(busy)) == capi.E_ARG
+    assert L.life_io_stats(None, None, None, None) == capi.E_ARG
+    assert capi.E_IO == 7 and capi.IO_SYNC == 0 and capi.IO_ASYNC == 1

@@ -2,7 +2,7 @@
 
 life_write_vtk / life_write_restart must produce, BYTE FOR BYTE, what GridClass::writeVTK (src/Grid.cpp:790-898) and
 GridClass::writeRestart (src/Grid.cpp:1163-1229) write from the same rho / u / f / force_ibm.  The expected bytes come from
-tests/vtkfile.py and tests/restartfile.py, which tests/test_output_files.py pins against the compiled reference's own writers
+oracle/fluidfiles.py (the numpy restatement of both formats), which tests/test_output_files.py pins against the compiled reference's own writers
 on the CPU; one test here also runs the compiled reference's writer and reader directly on the device's state / files.
 life_read_restart must be the exact inverse of life_write_restart and fail with the reference's messages.
 """

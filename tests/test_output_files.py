@@ -1,8 +1,8 @@
 """Pins the file-format restatements used as checkers of the device-fed file paths (include/life_b200.h, "device-fed files")
 against the compiled, unmodified reference's OWN writers and reader (oracle/_ref/libref_<case>.so):
 
-  tests/vtkfile.py      fluid_bytes()  == GridClass::writeVTK      (src/Grid.cpp:790-898), byte for byte
-  tests/restartfile.py  fluid_bytes()  == GridClass::writeRestart  (src/Grid.cpp:1163-1229), byte for byte
+  oracle/fluidfiles.py  vti_bytes()      == GridClass::writeVTK      (src/Grid.cpp:790-898), byte for byte
+  oracle/fluidfiles.py  restart_bytes()  == GridClass::writeRestart  (src/Grid.cpp:1163-1229), byte for byte
   life_vtk_frame()      (host half of life_write_vtk, no device needed) == the head / tail of the reference's .vti
   GridClass::readRestart accepts the restated bytes and recovers the state bit for bit
 

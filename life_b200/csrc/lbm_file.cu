@@ -38,6 +38,10 @@ namespace life {
 
 namespace {
 
+// both formats are written in the host's byte order and the reference swaps on big-endian hosts (src/Grid.cpp:793, :1172): this
+// library exists for little-endian B200 hosts only, and the .vti head says so
+static_assert(__BYTE_ORDER__ == __ORDER_LITTLE_ENDIAN__, "lbm_file.cu writes little-endian files");
+
 constexpr int RW = 15;   // 8-byte words per restart record: (i | j << 32), rho, ux, uy, fx, fy, f0..f8
 constexpr int64_t RESTART_HEAD = 44;   // int t, Nx, Ny; double omega, Dx, Dt, Dm (src/Grid.cpp:1183-1189), unpadded
 enum { JOB_VTK = 0, JOB_RESTART = 1 };

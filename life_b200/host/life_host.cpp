@@ -7,10 +7,11 @@
 //   GridClass::lbmKernel()            (src/Grid.cpp:36-100)     -> life_step
 //   ObjectsClass::ibmKernelInterp()   (src/Objects.cpp:102-117) -> life_ibm_set_markers + life_ibm_interp
 //   ObjectsClass::ibmKernelSpread()   (src/Objects.cpp:120-149) -> life_ibm_spread
-//   ObjectsClass::computeEpsilon()    (src/Objects.cpp:235-321), ONLY when the environment sets LIFE_B200_DEVICE_EPSILON
-//                                     (by default the reference's own host code runs, as the north star
-//                                     prescribes):  =1 -> life_ibm_assemble_epsilon (matrix on the GPU, bit-exact) + the
-//                                     reference's own Utils::solveLAPACK on the host (epsilon bit-identical to the reference);
+//   ObjectsClass::computeEpsilon()    (src/Objects.cpp:235-321), selected by LIFE_B200_DEVICE_EPSILON:
+//                                     =1 (default) -> life_ibm_assemble_epsilon: the O(n^2 * 9) delta evaluations of the matrix on the
+//                                     GPU (bit-exact), then the reference's own Utils::solveLAPACK on the host, as the north star
+//                                     prescribes for the solve: epsilon is bit-identical to the reference's;
+//                                     =0 -> the reference's own assembly + LAPACK solve, untouched;
 //                                     =2 -> life_ibm_compute_epsilon (assembly and LU both on the GPU);
 //                                     =3 -> per body: GPU LU for small systems (<= 64 markers, many of them: Honami), GPU
 //                                     assembly + host LAPACK for large ones (UNI_EPSILON: TurekHron 132, PELskin 310)
@@ -220,7 +221,7 @@ void send_markers(std::vector<IBMNodeClass> &iNode) {
 // ---- ObjectsClass::computeEpsilon (optional) ----------------------------------------------------------------------------------------
 void ObjectsClass::computeEpsilon() {
 	Timed timed(dev.t_eps);
-	static const int on_device = [] { const char *e = std::getenv("LIFE_B200_DEVICE_EPSILON"); return e ? std::atoi(e) : 0; }();
+	static const int on_device = [] { const char *e = std::getenv("LIFE_B200_DEVICE_EPSILON"); return e ? std::atoi(e) : 1; }();
 	if (!on_device || !dev.uploaded) {
 		// default, and always during construction (t = 0, before the first step creates the context): the reference's own
 		// assembly + LAPACK solve

@@ -133,3 +133,35 @@ def halo_plan(Nx, Ny, world, periodic_x):
         if left is not None and world > 1:
             plan.append((r, left, (2, 6, 8), 3 * Ny))      # cx = -1 leave through the left face
     return plan
+
+
+def file_plan(kind, Nx, Ny, world, rank, head_len=0, tail_len=0):
+    """Which bytes of the ONE shared fluid file rank `rank` writes (the design csrc/lbm_file.cu implements with pwrite(), stated on
+    the host so it can be checked without a GPU): a list of (file_offset, n_bytes, what), `what` naming the source:
+
+      kind "restart" (src/Grid.cpp:1163-1229): ("head",) 44 bytes by rank 0; ("records", i_begin, i_end) = the slab's 120-byte
+          records, one contiguous run because the file is i-major
+      kind "vti" (src/Grid.cpp:790-898): ("head",), ("size", block) x 3 and ("tail",) by rank 0; ("row", block, j) = this slab's
+          segment of row j of block 0 / 1 / 2 (Density, Pressure: 8 bytes per node; Velocity: 24), because the blocks are j-major
+    """
+    b, e = capi.slab_range(Nx, world, rank)
+    plan = []
+    if kind == "restart":
+        if rank == 0:
+            plan.append((0, 44, ("head",)))
+        plan.append((44 + b * Ny * 120, (e - b) * Ny * 120, ("records", b, e)))
+        return plan
+    if kind != "vti":
+        raise ValueError(kind)
+    n8 = Nx * Ny * 8
+    data = [head_len + 8, head_len + 8 + n8 + 8, head_len + 8 + 2 * (n8 + 8)]
+    if rank == 0:
+        plan.append((0, head_len, ("head",)))
+        for blk in range(3):
+            plan.append((data[blk] - 8, 8, ("size", blk)))
+        plan.append((data[2] + 3 * n8, tail_len, ("tail",)))
+    for blk in range(3):
+        comp8 = 24 if blk == 2 else 8
+        for j in range(Ny):
+            plan.append((data[blk] + (j * Nx + b) * comp8, (e - b) * comp8, ("row", blk, j)))
+    return plan

@@ -137,3 +137,80 @@ def test_halo_plan_is_exactly_what_leaves_a_slab():
         col = e - 1 if pops == (1, 5, 7) else b
         assert crossing[(s, d)] == {(col, v) for v in pops}
         assert n == 3 * Ny
+
+
+# ---- the shared-file design of the device-fed file paths (csrc/lbm_file.cu with nranks > 1) ----------------------------------------
+def _file_worker(rank, world, port, Nx, Ny, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from life_b200 import capi, dist as D
+    from oracle import fluidfiles as F
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(7)                      # every rank builds the same global state and keeps its slab
+        rho = 1.0 + 0.1 * rng.standard_normal((Nx, Ny))
+        u = 0.05 * rng.standard_normal((Nx, Ny, 2))
+        fi = 1e-3 * rng.standard_normal((Nx, Ny, 2))
+        f = rng.random((Nx, Ny, 9))
+        scal = dict(Dx=0.01, Dt=2e-4, Dm=1e-6, Drho=1.0)
+        b, e = capi.slab_range(Nx, world, rank)
+        head, tail = capi.vtk_frame(Nx, Ny, scal["Dx"])
+        # what this rank would have in its staging buffers: the file image of ITS slab only
+        my_vti = F.vti_bytes(rho[b:e], u[b:e], scal["Dx"], scal["Dt"], scal["Dm"], scal["Drho"], 1.0, 0.5)
+        h_loc, _ = F.vti_frame(e - b, Ny, scal["Dx"])
+        nl8 = (e - b) * Ny * 8
+        blocks = [my_vti[len(h_loc) + 8:len(h_loc) + 8 + nl8], my_vti[len(h_loc) + 16 + nl8:len(h_loc) + 16 + 2 * nl8],
+                  my_vti[len(h_loc) + 24 + 2 * nl8:len(h_loc) + 24 + 5 * nl8]]
+        my_rst = F.restart_bytes(3, 1.7, scal["Dx"], scal["Dt"], scal["Dm"], rho[b:e], u[b:e], fi[b:e], f[b:e])
+        # local record indices are slab-relative in that image: the device writes global i (k_restart_pack), so patch them
+        rec = np.frombuffer(bytearray(my_rst[44:]), dtype=F._NODE).copy()
+        rec["i"] += b
+        for kind, name in (("vti", "Fluid.3.vti"), ("restart", "Fluid.restart")):
+            path = os.path.join(out_dir, name)
+            fd = os.open(path, os.O_WRONLY | os.O_CREAT, 0o666)
+            for off, n, what in D.file_plan(kind, Nx, Ny, world, rank, len(head), len(tail)):
+                if what[0] == "head":
+                    data = head if kind == "vti" else F.restart_bytes(3, 1.7, scal["Dx"], scal["Dt"], scal["Dm"], rho, u, fi, f)[:44]
+                elif what[0] == "tail":
+                    data = tail
+                elif what[0] == "size":
+                    data = np.array([Nx * Ny * 8 * (3 if what[1] == 2 else 1)], "<u8").tobytes()
+                elif what[0] == "records":
+                    data = rec.tobytes()
+                else:
+                    _, blk, j = what
+                    w = (e - b) * (24 if blk == 2 else 8)
+                    data = blocks[blk][j * w:(j + 1) * w]
+                assert len(data) == n, (what, len(data), n)
+                os.pwrite(fd, data, off)
+            os.close(fd)
+        dist.barrier()
+        if rank == 0:
+            want = F.vti_bytes(rho, u, scal["Dx"], scal["Dt"], scal["Dm"], scal["Drho"], 1.0, 0.5)
+            assert open(os.path.join(out_dir, "Fluid.3.vti"), "rb").read() == want
+            want = F.restart_bytes(3, 1.7, scal["Dx"], scal["Dt"], scal["Dm"], rho, u, fi, f)
+            assert open(os.path.join(out_dir, "Fluid.restart"), "rb").read() == want
+            open(os.path.join(out_dir, "files_ok"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,shape", [(2, (12, 7)), (3, (13, 5))])
+def test_ranks_write_one_file_together_over_gloo(world, shape, tmp_path, lib_built):
+    """Every rank pwrite()s the byte ranges dist.file_plan gives it (what lbm_file.cu does with nranks > 1); the result must be
+    the reference's file of the whole lattice, byte for byte."""
+    import torch.multiprocessing as mp
+    Nx, Ny = shape
+    mp.spawn(_file_worker, args=(world, _free_port(), Nx, Ny, str(tmp_path)), nprocs=world, join=True)
+    assert (tmp_path / "files_ok").exists()
+
+
+def test_file_plan_tiles_the_file_exactly(lib_built):
+    from life_b200 import capi, dist as D
+    for Nx, Ny, world in ((12, 7, 2), (13, 5, 3), (64, 33, 8), (9, 4, 1)):
+        head, tail = capi.vtk_frame(Nx, Ny, 0.5)
+        for kind, total in (("vti", len(head) + 24 + 5 * 8 * Nx * Ny + len(tail)), ("restart", 44 + 120 * Nx * Ny)):
+            spans = sorted((off, off + n) for r in range(world) for off, n, _ in D.file_plan(kind, Nx, Ny, world, r, len(head), len(tail)))
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            for a, b in zip(spans, spans[1:]):
+                assert a[1] == b[0], (kind, Nx, Ny, world, a, b)      # no gap, no overlap

@@ -224,3 +224,79 @@ REF_API int ref_read_restart() {
 	return g_grid->tOffset;
 }
 REF_API double ref_ref_pressure() { return ref_P; }   // params.h: the constant writeVTK adds to the pressure
+
+// ---- flexible bodies (FEMBodyClass, src/FEMBody.cpp) ------------------------------------------------------------------------------
+// Read-only description + state vectors of the fb-th flexible body, and its dynamicFEM() alone: what the FEM restatement
+// (oracle/life_oracle_fem.c, groundwork for SURVEY.md §8f row 3) is initialised from and compared with.
+static IBMBodyClass *flex_body(int fb) {
+	int k = 0;
+	for (size_t ib = 0; ib < g_obj->iBody.size(); ib++)
+		if (g_obj->iBody[ib].flex == eFlexible && k++ == fb) return &g_obj->iBody[ib];
+	return nullptr;
+}
+REF_API int ref_fem_count() {
+	int k = 0;
+	for (size_t ib = 0; ib < g_obj->iBody.size(); ib++) k += g_obj->iBody[ib].flex == eFlexible;
+	return k;
+}
+// out: nNodes, nElements, bodyDOFs, bcDOFs, nIBM (= posMap.size()), total forceMap entries, simDOFs
+REF_API void ref_fem_dims(int fb, int *out) {
+	FEMBodyClass *s = flex_body(fb)->sBody;
+	int nmap = 0;
+	for (size_t e = 0; e < s->element.size(); e++) nmap += static_cast<int>(s->element[e].forceMap.size());
+	out[0] = static_cast<int>(s->node.size()); out[1] = static_cast<int>(s->element.size()); out[2] = s->bodyDOFs; out[3] = s->bcDOFs;
+	out[4] = static_cast<int>(s->posMap.size()); out[5] = nmap; out[6] = g_obj->simDOFs;
+}
+// params.h / grid constants the solver reads: alpha, delta, Dt, Dm, Dx, gravityX, gravityY, ref_L
+REF_API void ref_fem_constants(double *out) {
+	out[0] = alpha; out[1] = delta; out[2] = g_grid->Dt; out[3] = g_grid->Dm; out[4] = g_grid->Dx;
+	out[5] = gravityX; out[6] = gravityY; out[7] = ref_L;
+}
+// pos0 [2*nNodes], angle0 [nNodes]; el [nEl*5] = L0, A, I, E, rho per element
+REF_API void ref_fem_geometry(int fb, double *pos0, double *angle0, double *el) {
+	FEMBodyClass *s = flex_body(fb)->sBody;
+	for (size_t n = 0; n < s->node.size(); n++) {
+		pos0[2 * n] = s->node[n].pos0[eX]; pos0[2 * n + 1] = s->node[n].pos0[eY]; angle0[n] = s->node[n].angle0;
+	}
+	for (size_t e = 0; e < s->element.size(); e++) {
+		FEMElementClass &E = s->element[e];
+		el[5 * e] = E.L0; el[5 * e + 1] = E.A; el[5 * e + 2] = E.I; el[5 * e + 3] = E.E; el[5 * e + 4] = E.rho;
+	}
+}
+// posMap (per IBM node of the body: element, zeta), forceMap (per element: entries fm_first[e] .. fm_first[e+1]: body-local IBM
+// node, zeta1, zeta2), marker [nIBM] = index of the body's k-th IBM node in the global marker arrays
+REF_API void ref_fem_maps(int fb, int *pm_el, double *pm_zeta, int *fm_first, int *fm_node, double *fm_z1, double *fm_z2, int *marker) {
+	IBMBodyClass *b = flex_body(fb);
+	FEMBodyClass *s = b->sBody;
+	for (size_t i = 0; i < s->posMap.size(); i++) { pm_el[i] = s->posMap[i].elID; pm_zeta[i] = s->posMap[i].zeta; }
+	int k = 0;
+	for (size_t e = 0; e < s->element.size(); e++) {
+		fm_first[e] = k;
+		for (size_t n = 0; n < s->element[e].forceMap.size(); n++, k++) {
+			fm_node[k] = s->element[e].forceMap[n].nodeID; fm_z1[k] = s->element[e].forceMap[n].zeta1; fm_z2[k] = s->element[e].forceMap[n].zeta2;
+		}
+	}
+	fm_first[s->element.size()] = k;
+	for (size_t i = 0; i < b->node.size(); i++) marker[i] = static_cast<int>(b->node[i] - &g_obj->iNode[0]);
+}
+// state [11 * bodyDOFs]: U, Udot, Udotdot, U_n, Udot_n, Udotdot_n, U_km1, R_k, R_km1, U_nm1, U_nm2
+static const int FEM_VECS = 11;
+static std::vector<double> *fem_vectors(FEMBodyClass *s, int k) {
+	std::vector<double> *v[FEM_VECS] = {&s->U, &s->Udot, &s->Udotdot, &s->U_n, &s->Udot_n, &s->Udotdot_n, &s->U_km1, &s->R_k, &s->R_km1,
+	                                    &s->U_nm1, &s->U_nm2};
+	return v[k];
+}
+REF_API void ref_fem_get_state(int fb, double *out) {
+	FEMBodyClass *s = flex_body(fb)->sBody;
+	for (int k = 0; k < FEM_VECS; k++) memcpy(out + (size_t)k * s->bodyDOFs, fem_vectors(s, k)->data(), sizeof(double) * s->bodyDOFs);
+}
+REF_API void ref_fem_set_state(int fb, const double *in) {
+	FEMBodyClass *s = flex_body(fb)->sBody;
+	for (int k = 0; k < FEM_VECS; k++) memcpy(fem_vectors(s, k)->data(), in + (size_t)k * s->bodyDOFs, sizeof(double) * s->bodyDOFs);
+}
+// FEMBodyClass::dynamicFEM (src/FEMBody.cpp:26-68) of one body; out: subRes, subNum, subDen, resNR, itNR
+REF_API void ref_fem_dynamic(int fb, double *out) {
+	FEMBodyClass *s = flex_body(fb)->sBody;
+	s->dynamicFEM();
+	out[0] = s->subRes; out[1] = s->subNum; out[2] = s->subDen; out[3] = s->resNR; out[4] = s->itNR;
+}

@@ -152,6 +152,11 @@ class RefCase:
     def subres(self):
         return float(self.lib.ref_get_subres())
 
+    @property
+    def relax(self):
+        """ObjectsClass::relax, the Aitken relaxation factor of the current sub-iteration (src/Objects.cpp:178-188)"""
+        return float(self.lib.ref_get_relax())
+
     # ---- lattice state (reference layout: id = i*Ny + j) ----------------------------------------------------------
     def f(self):
         return self._get("f", (self.Nx, self.Ny, 9))
@@ -249,3 +254,40 @@ class RefCase:
     def read_restart(self):
         """GridClass::readRestart on <workdir>/Results/Restart/Fluid.restart; returns tOffset."""
         return self._in_workdir(self.lib.ref_read_restart)
+
+    # ---- flexible bodies (for the FEM restatement, oracle/life_oracle_fem.c) ----------------------------------------------
+    def fem_count(self):
+        return int(self.lib.ref_fem_count())
+
+    def fem_body(self, fb):
+        """Description of the fb-th flexible body as the reference built it (geometry, maps, constants)."""
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        d = np.zeros(7, np.int32)
+        self.lib.ref_fem_dims(int(fb), p(d))
+        nn, ne, ndof, nbc, nibm, nmap, sim = (int(x) for x in d)
+        c = np.zeros(8)
+        self.lib.ref_fem_constants(p(c))
+        pos0, angle0, el = np.zeros((nn, 2)), np.zeros(nn), np.zeros((ne, 5))
+        self.lib.ref_fem_geometry(int(fb), p(pos0), p(angle0), p(el))
+        pm_el, pm_zeta = np.zeros(nibm, np.int32), np.zeros(nibm)
+        fm_first, fm_node = np.zeros(ne + 1, np.int32), np.zeros(nmap, np.int32)
+        fm_z1, fm_z2, marker = np.zeros(nmap), np.zeros(nmap), np.zeros(nibm, np.int32)
+        self.lib.ref_fem_maps(int(fb), p(pm_el), p(pm_zeta), p(fm_first), p(fm_node), p(fm_z1), p(fm_z2), p(marker))
+        return dict(n_nodes=nn, n_el=ne, n_dof=ndof, n_bc=nbc, n_ibm=nibm, sim_dofs=sim, alpha=c[0], delta=c[1], Dt=c[2], Dm=c[3],
+                    Dx=c[4], gravityX=c[5], gravityY=c[6], ref_L=c[7], pos0=pos0, angle0=angle0, el=el, pm_el=pm_el, pm_zeta=pm_zeta,
+                    fm_first=fm_first, fm_node=fm_node, fm_z1=fm_z1, fm_z2=fm_z2, marker=marker)
+
+    def fem_get_state(self, fb, n_dof):
+        out = np.zeros((11, n_dof))     # U, Udot, Udotdot, U_n, Udot_n, Udotdot_n, U_km1, R_k, R_km1, U_nm1, U_nm2
+        self.lib.ref_fem_get_state(int(fb), out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def fem_set_state(self, fb, state):
+        state = np.ascontiguousarray(state, np.float64)
+        self.lib.ref_fem_set_state(int(fb), state.ctypes.data_as(C.c_void_p))
+
+    def fem_dynamic(self, fb):
+        """FEMBodyClass::dynamicFEM of one body -> (subRes, subNum, subDen, resNR, itNR)"""
+        out = np.zeros(5)
+        self.lib.ref_fem_dynamic(int(fb), out.ctypes.data_as(C.c_void_p))
+        return tuple(out[:4]) + (int(out[4]),)

@@ -79,7 +79,7 @@ r.close()
 print("OK")
 '''
 
-CASES = [("TurekHron", 25), ("InvertedFlag", 25), ("PELskin", 12), ("Honami", 6)]
+CASES = [("TurekHron", 80), ("InvertedFlag", 25), ("PELskin", 12), ("Honami", 6)]
 
 
 @pytest.mark.parametrize("case,steps", CASES, ids=[c for c, _ in CASES])

@@ -133,3 +133,80 @@ def test_serial_device_core_matches_the_reference(case, steps, host_core):
                        text=True, timeout=900, env=dict(os.environ, OPENBLAS_NUM_THREADS="1"))
     assert p.returncode == 0 and p.stdout.strip().endswith("OK"), p.stdout[-3000:] + p.stderr[-3000:]
     print(p.stdout.strip().splitlines()[-2])
+
+
+# ---- barrier placement: the CTA as real threads under ThreadSanitizer --------------------------------------------------------------
+RACE_SRC = os.path.join(ROOT, "tests", "native", "fem_core_race.cpp")
+RACE_EXE = os.path.join(ROOT, "tests", "native", "_build", "fem_core_race")
+
+RECORD = r'''
+import sys
+sys.path.insert(0, %(root)r)
+import numpy as np
+from oracle.refharness import RefCase
+case, steps, fb, out = %(case)r, %(steps)d, %(fb)d, %(out)r
+r = RefCase(case)
+d = r.fem_body(fb)
+ids, n = d["marker"], d["n_dof"]
+calls = []
+for step in range(steps):
+    r.t = r.t + 1
+    r.lbm_kernel()
+    r.subit = 0
+    while True:
+        before = r.fem_get_state(fb, n)
+        r.recompute_object_vals()
+        m = r.markers()
+        calls.append((1 if r.subit == 0 else 2, r.t, r.relax, before, m["force"][ids], m["epsilon"][ids]))
+        r.ibm_interp()
+        m = r.markers()
+        calls.append((0, r.t, 0.0, r.fem_get_state(fb, n), m["force"][ids], m["epsilon"][ids]))
+        r.fem_kernel()
+        r.subit = r.subit + 1
+        if not (r.subit < 20 and r.subres > r.subTol):
+            break
+    r.ibm_spread()
+with open(out, "wb") as f:
+    f.write(np.array([d["n_nodes"], d["n_bc"], d["n_ibm"], len(d["fm_node"]), len(calls)], "<i4").tobytes())
+    f.write(np.array([d["alpha"], d["delta"], d["Dt"], d["Dm"], d["gravityX"], d["gravityY"], d["ref_L"]], "<f8").tobytes())
+    for k in ("pos0", "angle0", "el"):
+        f.write(np.ascontiguousarray(d[k], "<f8").tobytes())
+    f.write(np.ascontiguousarray(d["pm_el"], "<i4").tobytes()); f.write(np.ascontiguousarray(d["pm_zeta"], "<f8").tobytes())
+    f.write(np.ascontiguousarray(d["fm_first"], "<i4").tobytes()); f.write(np.ascontiguousarray(d["fm_node"], "<i4").tobytes())
+    f.write(np.ascontiguousarray(d["fm_z1"], "<f8").tobytes()); f.write(np.ascontiguousarray(d["fm_z2"], "<f8").tobytes())
+    for kind, t, relax, st, force, eps in calls:
+        f.write(np.array([kind, t], "<i4").tobytes()); f.write(np.array([relax], "<f8").tobytes())
+        f.write(np.ascontiguousarray(st, "<f8").tobytes()); f.write(np.ascontiguousarray(force, "<f8").tobytes())
+        f.write(np.ascontiguousarray(eps, "<f8").tobytes())
+r.close()
+print("recorded %%d calls" %% len(calls))
+'''
+
+
+@pytest.fixture(scope="module")
+def race_exe():
+    os.makedirs(os.path.dirname(RACE_EXE), exist_ok=True)
+    if not os.path.exists(RACE_EXE) or os.path.getmtime(RACE_EXE) < max(os.path.getmtime(RACE_SRC), os.path.getmtime(CORE)):
+        r = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-ffp-contract=off", "-fsanitize=thread", "-Wall", "-Wextra", "-o", RACE_EXE,
+                            RACE_SRC, "-lpthread"], capture_output=True, text=True)
+        if r.returncode != 0:
+            pytest.skip("no ThreadSanitizer toolchain here: " + r.stderr[-300:])
+    return RACE_EXE
+
+
+@pytest.mark.parametrize("nthreads", [7, 32])
+@pytest.mark.parametrize("case,steps,fb", [("InvertedFlag", 12, 0), ("PELskin", 5, 3)], ids=["InvertedFlag", "PELskin"])
+def test_cta_of_real_threads_is_race_free_and_identical_to_serial(case, steps, fb, nthreads, race_exe, tmp_path):
+    """Every recorded call of a live run, executed by one thread and by a CTA of `nthreads` real threads (FEM_SYNC = pthread barrier)
+    under ThreadSanitizer: no data race reported, results bit-identical."""
+    if not refharness.available(case):
+        pytest.skip("oracle/_ref/libref_%s.so not built (make -C oracle ref)" % case)
+    calls = str(tmp_path / "calls.bin")
+    p = subprocess.run([sys.executable, "-c", RECORD % dict(root=ROOT, case=case, steps=steps, fb=fb, out=calls)], capture_output=True,
+                       text=True, timeout=900, env=dict(os.environ, OPENBLAS_NUM_THREADS="1"))
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    q = subprocess.run([race_exe, calls, str(nthreads)], capture_output=True, text=True, timeout=900,
+                       env=dict(os.environ, TSAN_OPTIONS="exitcode=66 halt_on_error=0"))
+    assert "ThreadSanitizer" not in q.stderr, q.stderr[:4000]
+    assert q.returncode == 0, q.stdout[-2000:] + q.stderr[-2000:]
+    print(q.stdout.strip())

@@ -276,6 +276,54 @@ int life_io_set_staging(life_ctx *ctx, int64_t bytes);
 int life_read_restart(life_ctx *ctx, const char *path, const double *force_xy, const double *u_in, const double *rho_in,
                       int32_t *t_out);
 
+/* ---- structural solver of the flexible bodies -------------------------------------------------------- */
+/*
+ * STATUS: not yet verified on a B200.  The solver core (csrc/fem_core.h) is checked on the CPU against the
+ * compiled reference — serially for its arithmetic, as real threads under ThreadSanitizer for its barriers — and these entry
+ * points are exercised by tests/test_gpu_fem.py, but no default path calls them: the host program keeps the reference's own FEM.
+ *
+ * One CTA per filament: FEMBodyClass::dynamicFEM (src/FEMBody.cpp:26-68: corotational 2-node beam elements, Newmark-beta,
+ * Newton-Raphson over a dense LU), resetValues + predictor (:341-349, :259-289) and the Aitken-relaxed update
+ * (src/Objects.cpp:195-208).  Marker forces / epsilon are read from, and marker positions / velocities written to, the device
+ * arrays of the immersed-boundary path (life_ibm_set_markers / life_ibm_interp), through each body's marker list.
+ */
+typedef struct life_fem_body {
+	int32_t n_nodes;              /* FEM nodes; elements = n_nodes - 1, DOFs = 3 * n_nodes (x, y, angle per node)              */
+	int32_t n_bc;                 /* leading DOFs removed by the boundary condition (3 = clamped, 2 = supported)               */
+	int32_t n_markers;            /* IBM markers of this body                                                                  */
+	double alpha, delta;          /* Newmark parameters                                                   (params.h:76-77)     */
+	double gravity_x, gravity_y;  /*                                                                      (params.h:57-58)     */
+	double ref_L;                 /* reference length of the Newton-Raphson residual                      (params.h:103)       */
+	const double *pos0;           /* [2 * n_nodes] initial node positions (physical units)                                     */
+	const double *angle0;         /* [n_nodes]                                                                                 */
+	const double *element;        /* [(n_nodes - 1) * 5] per element: L0, A, I, E, rho      (src/FEMElement.cpp:265-278)       */
+	const int32_t *marker;        /* [n_markers] index of the body's k-th marker in the arrays of life_ibm_set_markers         */
+	const int32_t *marker_element;/* [n_markers] posMap: element carrying the marker ...    (src/FEMBody.cpp:292-338)          */
+	const double *marker_zeta;    /* [n_markers]         ... and its local coordinate in [-1, 1]                               */
+	const int32_t *map_first;     /* [n_elements + 1] forceMap, CSR over elements: entries map_first[e] .. map_first[e+1]      */
+	const int32_t *map_marker;    /*   body-local marker loading the element ...                                                */
+	const double *map_zeta1, *map_zeta2;  /* ... over the local range [zeta1, zeta2]                                           */
+} life_fem_body;
+
+/* Builds the device image of n_bodies flexible bodies (replaces any previous set).  Dt and Dm come from the configuration. */
+int life_fem_create(life_ctx *ctx, int32_t n_bodies, const life_fem_body *bodies);
+
+/* The eleven state vectors of one body, [11 * 3 * n_nodes]: U, Udot, Udotdot, U_n, Udot_n, Udotdot_n, U_km1, R_k, R_km1, U_nm1, U_nm2. */
+int life_fem_set_state(life_ctx *ctx, int32_t body, const double *state);
+int life_fem_get_state(life_ctx *ctx, int32_t body, double *state);
+
+/* Start of time step t, sub-iteration 0: resetValues + predictor for every body; markers move accordingly.  Asynchronous. */
+int life_fem_predict(life_ctx *ctx, int32_t t);
+/* Later sub-iterations: U := U_km1 + relax * (U - U_km1), velocities and markers updated.  Asynchronous. */
+int life_fem_relax(life_ctx *ctx, double relax);
+/* dynamicFEM of every body with the marker forces of the last life_ibm_interp.  sums [3] = subRes, subNum, subDen added over the
+ * bodies in body order (ObjectsClass::femKernel, src/Objects.cpp:63-98); per_body [5 * n_bodies] = subRes, subNum, subDen, resNR,
+ * itNR of each (may be NULL).  Synchronises. */
+int life_fem_dynamic(life_ctx *ctx, double *sums, double *per_body);
+
+/* Marker positions / velocities as the device holds them (after life_fem_*), [2 * n] each; either may be NULL. */
+int life_ibm_get_markers(life_ctx *ctx, double *pos, double *vel);
+
 /* ---- test hooks (bit-exact integer-map checks)------------------------------------------------------------------------ */
 
 /* Supports as IBMNodeClass::supp holds them: count [n]; idx, jdx, dirac [n*9] in the reference's i-outer/j-inner order. */

@@ -17,7 +17,7 @@ OBJ = os.path.join(HERE, "lib", "obj")
 LIB = os.path.join(HERE, "lib", "liblife_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
-SOURCES = ["api.cu", "lbm_bulk.cu", "lbm_boundary.cu", "lbm_io.cu", "lbm_file.cu", "halo.cu", "ibm.cu", "ibm_eps.cu", "nccl_dyn.cu"]
+SOURCES = ["api.cu", "lbm_bulk.cu", "lbm_boundary.cu", "lbm_io.cu", "lbm_file.cu", "halo.cu", "ibm.cu", "ibm_eps.cu", "fem.cu", "nccl_dyn.cu"]
 
 NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 # sm_100a only (B200); -lineinfo so ncu's source page maps to these files.  The host compiler is the system g++.

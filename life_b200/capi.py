@@ -30,6 +30,8 @@ EXPORTS = [
     "life_bulk_kernel_ms", "life_set_profiling",
     "life_vtk_frame", "life_write_vtk", "life_write_restart", "life_io_wait", "life_io_busy", "life_io_stats", "life_io_set_staging",
     "life_read_restart",
+    "life_fem_create", "life_fem_set_state", "life_fem_get_state", "life_fem_predict", "life_fem_relax", "life_fem_dynamic",
+    "life_ibm_get_markers",
 ]
 
 
@@ -62,6 +64,16 @@ class Config(C.Structure):
             if not hasattr(self, k):
                 raise AttributeError(k)
             setattr(self, k, v)
+
+
+class FemBody(C.Structure):
+    """struct life_fem_body"""
+    _fields_ = [("n_nodes", C.c_int32), ("n_bc", C.c_int32), ("n_markers", C.c_int32),
+                ("alpha", C.c_double), ("delta", C.c_double), ("gravity_x", C.c_double), ("gravity_y", C.c_double),
+                ("ref_L", C.c_double),
+                ("pos0", C.c_void_p), ("angle0", C.c_void_p), ("element", C.c_void_p),
+                ("marker", C.c_void_p), ("marker_element", C.c_void_p), ("marker_zeta", C.c_void_p),
+                ("map_first", C.c_void_p), ("map_marker", C.c_void_p), ("map_zeta1", C.c_void_p), ("map_zeta2", C.c_void_p)]
 
 
 class LifeError(RuntimeError):
@@ -124,6 +136,13 @@ def load():
     L.life_io_stats.argtypes = [vp, C.POINTER(dbl), C.POINTER(i64), C.POINTER(i32)]
     L.life_io_set_staging.argtypes = [vp, i64]
     L.life_read_restart.argtypes = [vp, C.c_char_p, vp, vp, vp, C.POINTER(i32)]
+    L.life_fem_create.argtypes = [vp, i32, vp]
+    L.life_fem_set_state.argtypes = [vp, i32, vp]
+    L.life_fem_get_state.argtypes = [vp, i32, vp]
+    L.life_fem_predict.argtypes = [vp, i32]
+    L.life_fem_relax.argtypes = [vp, dbl]
+    L.life_fem_dynamic.argtypes = [vp, vp, vp]
+    L.life_ibm_get_markers.argtypes = [vp, vp, vp]
     _lib = L
     return L
 
@@ -344,6 +363,54 @@ class Context:
         t = C.c_int32()
         self._ck(self.L.life_read_restart(self.h, os.fsencode(path), _ptr(fxy), _ptr(u_in), _ptr(rho_in), C.byref(t)))
         return t.value
+
+    # ---- structural solver of the flexible bodies (not yet verified on a B200, see include/life_b200.h) ----
+    def fem_create(self, bodies):
+        """bodies: list of dicts with n_nodes, n_bc, alpha, delta, gravityX, gravityY, ref_L, pos0, angle0, el, marker, pm_el, pm_zeta,
+        fm_first, fm_node, fm_z1, fm_z2 (one dict per body, keys as in struct life_fem_body: see tests/test_gpu_fem.py)"""
+        arr = (FemBody * len(bodies))()
+        self._fem_keep = []
+        self._fem_dofs = []
+        for k, d in enumerate(bodies):
+            f64 = {n: np.ascontiguousarray(d[n], np.float64) for n in ("pos0", "angle0", "el", "pm_zeta", "fm_z1", "fm_z2")}
+            i32 = {n: np.ascontiguousarray(d[n], np.int32) for n in ("marker", "pm_el", "fm_first", "fm_node")}
+            self._fem_keep.append((f64, i32))
+            b = arr[k]
+            b.n_nodes, b.n_bc, b.n_markers = int(d["n_nodes"]), int(d["n_bc"]), len(i32["marker"])
+            b.alpha, b.delta, b.gravity_x, b.gravity_y, b.ref_L = (float(d[n]) for n in ("alpha", "delta", "gravityX", "gravityY", "ref_L"))
+            b.pos0, b.angle0, b.element = (f64[n].ctypes.data for n in ("pos0", "angle0", "el"))
+            b.marker, b.marker_element, b.marker_zeta = i32["marker"].ctypes.data, i32["pm_el"].ctypes.data, f64["pm_zeta"].ctypes.data
+            b.map_first, b.map_marker = i32["fm_first"].ctypes.data, i32["fm_node"].ctypes.data
+            b.map_zeta1, b.map_zeta2 = f64["fm_z1"].ctypes.data, f64["fm_z2"].ctypes.data
+            self._fem_dofs.append(3 * int(d["n_nodes"]))
+        self._ck(self.L.life_fem_create(self.h, len(bodies), C.cast(arr, C.c_void_p)))
+
+    def fem_set_state(self, body, state):
+        state = np.ascontiguousarray(state, np.float64)
+        assert state.shape == (11, self._fem_dofs[body])
+        self._ck(self.L.life_fem_set_state(self.h, int(body), _ptr(state)))
+
+    def fem_get_state(self, body):
+        st = np.zeros((11, self._fem_dofs[body]))
+        self._ck(self.L.life_fem_get_state(self.h, int(body), _ptr(st)))
+        return st
+
+    def fem_predict(self, t):
+        self._ck(self.L.life_fem_predict(self.h, int(t)))
+
+    def fem_relax(self, relax):
+        self._ck(self.L.life_fem_relax(self.h, float(relax)))
+
+    def fem_dynamic(self):
+        """-> (sums [subRes, subNum, subDen], per-body array [n_bodies, 5] = subRes, subNum, subDen, resNR, itNR)"""
+        sums, per = np.zeros(3), np.zeros((len(self._fem_dofs), 5))
+        self._ck(self.L.life_fem_dynamic(self.h, _ptr(sums), _ptr(per)))
+        return sums, per
+
+    def ibm_get_markers(self):
+        pos, vel = np.zeros((self.n_markers, 2)), np.zeros((self.n_markers, 2))
+        self._ck(self.L.life_ibm_get_markers(self.h, _ptr(pos), _ptr(vel)))
+        return pos, vel
 
     # ---- test / measurement hooks ----
     def boundary(self):

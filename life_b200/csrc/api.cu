@@ -48,6 +48,7 @@ static void free_ctx(life_ctx *ctx) {
 	cudaSetDevice(ctx->device);
 	if (ctx->io) { io_wait(ctx); io_free(ctx); }   // completes a pending asynchronous file write first
 	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+	fem_free(ctx);
 	ibm_free(ctx);
 	if (ctx->comm) ncclCommDestroy(ctx->comm);
 	cudaFree(ctx->fA); cudaFree(ctx->fB); cudaFree(ctx->macro); cudaFree(ctx->fibm); cudaFree(ctx->fxyf);

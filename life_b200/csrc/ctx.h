@@ -67,6 +67,7 @@ struct MarkerBuffers {
 };
 
 struct IoState;   // lbm_file.cu
+struct FemState;  // fem.cu
 
 }  // namespace life
 
@@ -112,6 +113,7 @@ struct life_ctx {
 
 	life::MarkerBuffers mk;
 	life::IoState *io = nullptr;          // staging, snapshot and worker of the device-fed file paths (lbm_file.cu)
+	life::FemState *fem = nullptr;        // flexible bodies of the device structural solver (fem.cu)
 	double *scratch = nullptr;            // device staging for upload / download
 	size_t scratch_bytes = 0;
 	double *d_red = nullptr;              // reduction scratch (max speed etc.)
@@ -174,6 +176,8 @@ void ibm_free(life_ctx *ctx);
 int ibm_compute_epsilon(life_ctx *ctx, int64_t nb, const int64_t *first, const int64_t *members, double *eps_out);
 int ibm_assemble_epsilon(life_ctx *ctx, int64_t nb, const int64_t *first, const int64_t *members, double *A_out);
 
+// fem.cu
+void fem_free(life_ctx *ctx);
 // lbm_file.cu
 int io_wait(life_ctx *ctx);
 void io_free(life_ctx *ctx);

@@ -98,3 +98,19 @@ def test_file_entry_points_reject_bad_arguments_without_a_device(lib_built):
     assert L.life_io_busy(None, C.byref(busy)) == capi.E_ARG
     assert L.life_io_stats(None, None, None, None) == capi.E_ARG
     assert capi.E_IO == 7 and capi.IO_SYNC == 0 and capi.IO_ASYNC == 1
+
+
+def test_fem_body_struct_layout_matches_the_header(tmp_path):
+    """ctypes mirror of struct life_fem_body == the C layout (offsets printed by a program compiled against include/life_b200.h)."""
+    import subprocess
+    from life_b200 import capi
+    fields = [n for n, _ in capi.FemBody._fields_]
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "life_b200.h"\nint main(void) {\n' +
+                   "".join('  printf("%%zu\\n", offsetof(life_fem_body, %s));\n' % n for n in fields) +
+                   '  printf("%zu\\n", sizeof(life_fem_body));\n  return 0;\n}\n')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    out = [int(x) for x in subprocess.check_output([str(exe)], text=True).split()]
+    assert out[:-1] == [getattr(capi.FemBody, n).offset for n in fields]
+    assert out[-1] == __import__("ctypes").sizeof(capi.FemBody)

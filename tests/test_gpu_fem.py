@@ -1,0 +1,132 @@
+"""First device run of the structural solver (life_fem_* of include/life_b200.h; csrc/fem.cu over csrc/fem_core.h; SURVEY.md §8f
+row 3).  The solver's arithmetic and barrier placement are verified on the CPU (tests/test_fem_core.py) and it is compiled into
+the library, but this round's GPU budget was spent before it was written, so it HAS NOT RUN ON A B200 YET: these tests are marked
+xfail(strict=False) — an XPASS in the driver's round-end run is the first confirmation, a failure is information for the next
+round, and neither takes the suite down.  Each case runs in a subprocess so that a fault cannot poison the CUDA context of the
+other tests.
+
+Method = tests/test_fem_core.py with the device in place of the serial host build: inside live fluid-structure runs of the
+compiled reference, every predictor / relaxed update / dynamicFEM call of every flexible body is repeated through the C ABI from
+the reference's state; marker positions and velocities (read back with life_ibm_get_markers), state vectors and residual sums must
+agree to rounding (own LU instead of LAPACK: 1e-11 of the body length for displacements, 1e-8 for velocities / accelerations /
+residual sums).
+"""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from oracle import refharness
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SCRIPT = r'''
+import sys
+sys.path.insert(0, %(root)r)
+import numpy as np
+from oracle.refharness import RefCase
+from life_b200 import capi
+from tests import cases as K
+case, steps = %(case)r, %(steps)d
+r = RefCase(case)
+g = K.golden(case)
+o = K.make_oracle(g)
+ctx = capi.Context(K.life_config(o.params, o, device=0))
+assert (ctx.cfg.Dt, ctx.cfg.Dm) == (r.Dt, r.Dm)
+nb = r.fem_count()
+desc = [r.fem_body(fb) for fb in range(nb)]
+def send(m):
+    ctx.ibm_set_markers(m["pos"], m["vel"], m["ds"], m["epsilon"])
+    ctx.ibm_set_forces(m["force"])
+send(r.markers())
+ctx.fem_create(desc)
+worst = {}
+def close(a, b, what, scale_floor, tol=1e-11):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    err = float(np.abs(a - b).max() / max(np.abs(b).max(), scale_floor))
+    worst[what] = max(worst.get(what, 0.0), err)
+    assert err < tol, (what, err)
+calls = 0
+for step in range(steps):
+    r.t = r.t + 1
+    r.lbm_kernel()
+    r.subit = 0
+    while True:
+        # ---- predictor / relaxed update of every body in one launch
+        m0 = r.markers()
+        for fb in range(nb):
+            ctx.fem_set_state(fb, r.fem_get_state(fb, desc[fb]["n_dof"]))
+        send(m0)
+        r.recompute_object_vals()
+        m = r.markers()
+        if r.subit == 0:
+            ctx.fem_predict(r.t)
+        else:
+            ctx.fem_relax(r.relax)
+        pos, vel = ctx.ibm_get_markers()
+        rigid = np.ones(len(pos), bool)
+        for fb in range(nb):
+            d, ids = desc[fb], desc[fb]["marker"]
+            rigid[ids] = False
+            close(pos[ids], m["pos"][ids], "predict/relax marker pos", d["ref_L"])
+            close(vel[ids], m["vel"][ids], "predict/relax marker vel", d["ref_L"] / d["Dt"] * 1e-3, 1e-8)
+            got, ref_st = ctx.fem_get_state(fb), r.fem_get_state(fb, d["n_dof"])
+            for k in (0, 3, 6, 9, 10):
+                close(got[k], ref_st[k], "predict/relax displacement vectors", d["ref_L"])
+            for k, s in ((1, 1.0 / d["Dt"]), (2, 1.0 / d["Dt"] ** 2), (4, 1.0 / d["Dt"]), (5, 1.0 / d["Dt"] ** 2)):
+                close(got[k], ref_st[k], "predict/relax velocity / acceleration vectors", d["ref_L"] * s * 1e-3, 1e-8)
+        assert np.array_equal(pos[rigid], m0["pos"][rigid]) and np.array_equal(vel[rigid], m0["vel"][rigid])   # other markers untouched
+        # ---- dynamicFEM of every body in one launch
+        r.ibm_interp()
+        m = r.markers()
+        before = [r.fem_get_state(fb, desc[fb]["n_dof"]) for fb in range(nb)]
+        for fb in range(nb):
+            ctx.fem_set_state(fb, before[fb])
+        send(m)
+        sums, per = ctx.fem_dynamic()
+        pos, vel = ctx.ibm_get_markers()
+        ref_sums = np.zeros(3)
+        for fb in range(nb):
+            d, ids = desc[fb], desc[fb]["marker"]
+            ref_res = r.fem_dynamic(fb)
+            after = r.fem_get_state(fb, d["n_dof"])
+            m2 = r.markers()
+            ref_sums += np.array(ref_res[:3])
+            assert abs(int(per[fb, 4]) - ref_res[4]) <= 1, ("Newton-Raphson iterations", per[fb], ref_res)
+            got = ctx.fem_get_state(fb)
+            close(got[0], after[0], "U after dynamicFEM", d["ref_L"])
+            close(got[1], after[1], "Udot after dynamicFEM", d["ref_L"] / d["Dt"] * 1e-3, 1e-8)
+            close(got[2], after[2], "Udotdot after dynamicFEM", d["ref_L"] / d["Dt"] ** 2 * 1e-3, 1e-8)
+            close(got[7], after[7], "R_k", d["ref_L"]); close(got[8], after[8], "R_km1", d["ref_L"])
+            close(pos[ids], m2["pos"][ids], "marker pos", d["ref_L"])
+            close(vel[ids], m2["vel"][ids], "marker vel", d["ref_L"] / d["Dt"] * 1e-3, 1e-8)
+            close(per[fb, :3], ref_res[:3], "subRes, subNum, subDen", d["ref_L"] ** 2 * 1e-6, 1e-8)
+            r.fem_set_state(fb, before[fb])
+            calls += 1
+        close(sums, ref_sums, "sums over the bodies", desc[0]["ref_L"] ** 2 * 1e-6, 1e-8)
+        r.set_marker_posvel(m["pos"], m["vel"])
+        r.fem_kernel()
+        r.subit = r.subit + 1
+        if not (r.subit < 20 and r.subres > r.subTol):
+            break
+    r.ibm_spread()
+print("%%s: %%d bodies, %%d steps, %%d dynamicFEM calls on the device, %%d kernel launches; worst relative differences: %%s"
+      %% (case, nb, steps, calls, ctx.launch_count(), {k: float("%%.1e" %% v) for k, v in worst.items()}))
+ctx.close(); r.close()
+print("OK")
+'''
+
+CASES = [("TurekHron", 40), ("InvertedFlag", 25), ("PELskin", 12), ("Honami", 6)]
+
+
+@pytest.mark.xfail(strict=False, reason="first execution of csrc/fem.cu on a B200 (verified on the CPU only so far, see the module docstring)")
+@pytest.mark.parametrize("case,steps", CASES, ids=[c for c, _ in CASES])
+def test_device_structural_solver_matches_the_reference(case, steps):
+    if not refharness.available(case):
+        pytest.skip("oracle/_ref/libref_%s.so not built" % case)
+    p = subprocess.run([sys.executable, "-c", SCRIPT % dict(root=ROOT, case=case, steps=steps)], capture_output=True, text=True,
+                       timeout=900, env=dict(os.environ, OPENBLAS_NUM_THREADS="1"))
+    print(p.stdout[-1500:])
+    assert p.returncode == 0 and p.stdout.strip().endswith("OK"), p.stdout[-3000:] + p.stderr[-3000:]

@@ -278,9 +278,10 @@ int life_read_restart(life_ctx *ctx, const char *path, const double *force_xy, c
 
 /* ---- structural solver of the flexible bodies -------------------------------------------------------- */
 /*
- * STATUS: not yet verified on a B200.  The solver core (csrc/fem_core.h) is checked on the CPU against the
- * compiled reference — serially for its arithmetic, as real threads under ThreadSanitizer for its barriers — and these entry
- * points are exercised by tests/test_gpu_fem.py, but no default path calls them: the host program keeps the reference's own FEM.
+ * STATUS: new.  The solver core (csrc/fem_core.h) is checked on the CPU against the compiled reference — serially
+ * for its arithmetic, as real threads under ThreadSanitizer for its barriers —, these entry points are exercised by
+ * tests/test_gpu_fem.py and first short runs on a B200 agree with the reference to rounding; no default path calls them yet: the
+ * host program keeps the reference's own FEM.
  *
  * One CTA per filament: FEMBodyClass::dynamicFEM (src/FEMBody.cpp:26-68: corotational 2-node beam elements, Newmark-beta,
  * Newton-Raphson over a dense LU), resetValues + predictor (:341-349, :259-289) and the Aitken-relaxed update

@@ -1,9 +1,10 @@
 // The structural solver of the flexible bodies on the device: one CTA per filament running fem_core.h.
 //
 // STATUS: compiled into the library, its logic and barrier placement are checked on the CPU (tests/test_fem_core.py: the same
-// source run serially and as real threads under ThreadSanitizer against the compiled reference), but it has NOT yet run on a
-// B200 — the round's GPU budget was spent before it was written.  Nothing in the default paths calls it: the host program keeps
-// the reference's own FEM (life_host.cpp does not bind femKernel yet).  tests/test_gpu_fem.py is its first device run.
+// source run serially and as real threads under ThreadSanitizer against the compiled reference) and two short first runs on a
+// B200 agree with the reference to rounding (profiles/r01_fem_first_device_runs.txt: InvertedFlag; Honami, 128 filaments); the
+// full device tests are tests/test_gpu_fem.py.  Nothing in the default paths calls it yet: the host program keeps the reference's
+// own FEM (life_host.cpp does not bind femKernel).
 //
 // Data: every body's constant description, geometry, dense M / K (dim^2 doubles each; 63 x 63 = 31 KB: L2-resident) and state
 // vectors live in one device arena; `Body` views (pointers into it) sit in a device array indexed by blockIdx.x.  The marker

@@ -15,6 +15,13 @@
 //                                     =2 -> life_ibm_compute_epsilon (assembly and LU both on the GPU);
 //                                     =3 -> per body: GPU LU for small systems (<= 64 markers, many of them: Honami), GPU
 //                                     assembly + host LAPACK for large ones (UNI_EPSILON: TurekHron 132, PELskin 310)
+//   ObjectsClass::recomputeObjectVals / femKernel (src/Objects.cpp:152-232, :63-98), ONLY with
+//                                     LIFE_B200_DEVICE_FEM=1 (off by default: the device solver has had its first B200 runs through
+//                                     the C ABI, tests/test_gpu_fem.py, but THIS binding has not run yet — DESIGN.md §10):
+//                                     predictor / relaxed update / dynamicFEM of all flexible bodies on the device
+//                                     (life_fem_predict / _relax / _dynamic), one CTA per filament; the host's FEM state and marker
+//                                     positions are refreshed from the device after each call, so every host writer and the
+//                                     support / ds / epsilon code keep working unchanged
 //   GridClass::writeInfo / writeVTK / writeRestart / readRestart (src/Grid.cpp:559, :790, :1163, :1072), SURVEY.md §8f row 2:
 //                                     the device-fed file paths — life_max_speed for the scan of writeInfo, life_write_vtk and
 //                                     life_write_restart (asynchronous: the time loop goes on while the file is written) produce
@@ -41,6 +48,7 @@
 #include "Grid.h"
 #include "Objects.h"
 #include "Utils.h"
+#include "FEMBody.h"
 #include "life_b200.h"
 #include <dlfcn.h>
 #include <chrono>
@@ -61,6 +69,8 @@ struct DeviceSide {
 	// wall-clock accounting (seconds spent inside each replaced body; the rest of the program is the reference's host code)
 	double t_step = 0, t_interp = 0, t_spread = 0, t_eps = 0, t_io = 0, t_first = 0, t_begin = 0;
 	double t_info = 0, t_vtk = 0, t_restart = 0;   // parts of t_io
+	double t_fem = 0;   // inside the optional device FEM bindings
+	long fem_calls = 0;
 } dev;
 
 double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -145,6 +155,7 @@ void report() {
 		std::fprintf(stderr, "\n[life_b200] steady state %.1f us per time step = %.1f MLUPS (%ld x %ld lattice, %ld steps, all host work and output included)",
 		             1e6 * (wall - dev.t_first) / (double)dev.steps, (double)Nx * Ny * dev.steps / (wall - dev.t_first) / 1e6,
 		             (long)Nx, (long)Ny, dev.steps);
+	if (dev.fem_calls) std::fprintf(stderr, "\n[life_b200] device FEM: %ld life_fem_dynamic calls, %.3f s inside the FEM bindings", dev.fem_calls, dev.t_fem);
 	std::fprintf(stderr, "\n[life_b200] %ld life_step, %ld life_ibm_interp, %ld life_ibm_spread, %ld life_ibm_compute_epsilon, %lld kernel launches\n",
 	             dev.steps, dev.interps, dev.spreads, dev.eps_solves, (long long)life_launch_count(dev.ctx));
 	life_destroy(dev.ctx);
@@ -276,6 +287,153 @@ void ObjectsClass::computeEpsilon() {
 		}
 	}
 	dev.eps_solves++;
+}
+
+// ---- ObjectsClass::recomputeObjectVals / femKernel (optional, LIFE_B200_DEVICE_FEM=1) ------------------------------------------------
+namespace {
+
+bool device_fem() {
+	static const bool on = [] { const char *e = std::getenv("LIFE_B200_DEVICE_FEM"); return e && std::atoi(e) != 0; }();
+	return on;
+}
+
+struct DeviceFem {
+	bool ready = false;
+	std::vector<IBMBodyClass *> body;      // the flexible bodies, in iBody order (= the order femKernel adds their residuals)
+	std::vector<double> state, pos, vel, per_body;
+} dfem;
+
+std::vector<double> *fem_vector(FEMBodyClass *s, int k) {   // the order of life_fem_set_state / life_fem_get_state
+	std::vector<double> *v[11] = {&s->U, &s->Udot, &s->Udotdot, &s->U_n, &s->Udot_n, &s->Udotdot_n, &s->U_km1, &s->R_k, &s->R_km1, &s->U_nm1, &s->U_nm2};
+	return v[k];
+}
+
+// describe the reference's flexible bodies to the library (once) and hand over their current state
+void fem_setup(ObjectsClass &o) {
+	if (dfem.ready) return;
+	std::vector<life_fem_body> desc;
+	std::vector<std::vector<double>> dbl;
+	std::vector<std::vector<int32_t>> ints;
+	for (size_t ib = 0; ib < o.iBody.size(); ib++)
+		if (o.iBody[ib].flex == eFlexible) dfem.body.push_back(&o.iBody[ib]);
+	dbl.reserve(dfem.body.size() * 6);
+	ints.reserve(dfem.body.size() * 4);
+	for (IBMBodyClass *b : dfem.body) {
+		FEMBodyClass *s = b->sBody;
+		const size_t n = s->node.size(), ne = s->element.size();
+		std::vector<double> pos0(2 * n), angle0(n), el(5 * ne), pz(s->posMap.size()), z1, z2;
+		std::vector<int32_t> mk(b->node.size()), pe(s->posMap.size()), first(ne + 1, 0), fm;
+		for (size_t i = 0; i < n; i++) { pos0[2 * i] = s->node[i].pos0[eX]; pos0[2 * i + 1] = s->node[i].pos0[eY]; angle0[i] = s->node[i].angle0; }
+		for (size_t e = 0; e < ne; e++) {
+			const FEMElementClass &E = s->element[e];
+			el[5 * e] = E.L0; el[5 * e + 1] = E.A; el[5 * e + 2] = E.I; el[5 * e + 3] = E.E; el[5 * e + 4] = E.rho;
+			first[e] = (int32_t)fm.size();
+			for (size_t k = 0; k < E.forceMap.size(); k++) { fm.push_back(E.forceMap[k].nodeID); z1.push_back(E.forceMap[k].zeta1); z2.push_back(E.forceMap[k].zeta2); }
+		}
+		first[ne] = (int32_t)fm.size();
+		for (size_t i = 0; i < s->posMap.size(); i++) { pe[i] = s->posMap[i].elID; pz[i] = s->posMap[i].zeta; }
+		for (size_t i = 0; i < b->node.size(); i++) mk[i] = (int32_t)(b->node[i] - &o.iNode[0]);
+		life_fem_body d{};
+		d.n_nodes = (int32_t)n; d.n_bc = s->bcDOFs; d.n_markers = (int32_t)b->node.size();
+		d.alpha = alpha; d.delta = delta; d.gravity_x = gravityX; d.gravity_y = gravityY; d.ref_L = ref_L;
+		dbl.push_back(std::move(pos0)); d.pos0 = dbl.back().data();
+		dbl.push_back(std::move(angle0)); d.angle0 = dbl.back().data();
+		dbl.push_back(std::move(el)); d.element = dbl.back().data();
+		dbl.push_back(std::move(pz)); d.marker_zeta = dbl.back().data();
+		dbl.push_back(std::move(z1)); d.map_zeta1 = dbl.back().data();
+		dbl.push_back(std::move(z2)); d.map_zeta2 = dbl.back().data();
+		ints.push_back(std::move(mk)); d.marker = ints.back().data();
+		ints.push_back(std::move(pe)); d.marker_element = ints.back().data();
+		ints.push_back(std::move(first)); d.map_first = ints.back().data();
+		ints.push_back(std::move(fm)); d.map_marker = ints.back().data();
+		desc.push_back(d);
+	}
+	send_markers(o.iNode);     // the marker arrays the solver reads and writes must exist on the device
+	LIFE_CK(life_fem_create(dev.ctx, (int32_t)desc.size(), desc.data()));
+	for (size_t k = 0; k < dfem.body.size(); k++) {
+		FEMBodyClass *s = dfem.body[k]->sBody;
+		dfem.state.resize(11 * (size_t)s->bodyDOFs);
+		for (int v = 0; v < 11; v++) std::copy(fem_vector(s, v)->begin(), fem_vector(s, v)->end(), dfem.state.begin() + (size_t)v * s->bodyDOFs);
+		LIFE_CK(life_fem_set_state(dev.ctx, (int32_t)k, dfem.state.data()));
+	}
+	dfem.ready = true;
+}
+
+// device -> host: FEM state vectors (and the geometry that follows from U), marker positions and velocities of the flexible bodies
+void fem_refresh_host(ObjectsClass &o) {
+	const size_t nm = o.iNode.size();
+	dfem.pos.resize(2 * nm); dfem.vel.resize(2 * nm);
+	LIFE_CK(life_ibm_get_markers(dev.ctx, dfem.pos.data(), dfem.vel.data()));
+	for (size_t k = 0; k < dfem.body.size(); k++) {
+		IBMBodyClass *b = dfem.body[k];
+		FEMBodyClass *s = b->sBody;
+		dfem.state.resize(11 * (size_t)s->bodyDOFs);
+		LIFE_CK(life_fem_get_state(dev.ctx, (int32_t)k, dfem.state.data()));
+		for (int v = 0; v < 11; v++) std::copy(dfem.state.begin() + (size_t)v * s->bodyDOFs, dfem.state.begin() + (size_t)(v + 1) * s->bodyDOFs, fem_vector(s, v)->begin());
+		s->updateFEMValues();
+		for (size_t i = 0; i < b->node.size(); i++) {
+			const size_t g = (size_t)(b->node[i] - &o.iNode[0]);
+			b->node[i]->pos[eX] = dfem.pos[2 * g]; b->node[i]->pos[eY] = dfem.pos[2 * g + 1];
+			b->node[i]->vel[eX] = dfem.vel[2 * g]; b->node[i]->vel[eY] = dfem.vel[2 * g + 1];
+		}
+	}
+}
+
+}  // namespace
+
+void ObjectsClass::recomputeObjectVals() {
+	if (!device_fem() || !dev.uploaded) {
+		using Fn = void (*)(ObjectsClass *);
+		static Fn orig = next_symbol<Fn>("_ZN12ObjectsClass19recomputeObjectValsEv");
+		orig(this);
+		return;
+	}
+	{
+		Timed timed(dev.t_fem);
+		fem_setup(*this);
+		if (subIt == 0) {
+			LIFE_CK(life_fem_predict(dev.ctx, gPtr->t));                       // resetValues + predictor, src/Objects.cpp:160-174
+		} else {
+			if (subIt == 1) relax = static_cast<double>(Utils::sgn(relax) * min(fabs(relax), relaxMax));   // src/Objects.cpp:183-188
+			else relax = -relax * subNum / subDen;
+			LIFE_CK(life_fem_relax(dev.ctx, relax));                           // src/Objects.cpp:195-208
+		}
+		fem_refresh_host(*this);
+	}
+	// supports and ds of the moved markers, then epsilon: the reference's own host code (src/Objects.cpp:214-231)
+#pragma omp parallel for schedule(guided)
+	for (size_t i = 0; i < iNode.size(); i++) {
+		if (iNode[i].iPtr->flex == eFlexible) {
+			iNode[i].findSupport();
+			iNode[i].computeDs();
+		}
+	}
+	computeEpsilon();
+}
+
+void ObjectsClass::femKernel() {
+	if (!device_fem() || !dev.uploaded) {
+		using Fn = void (*)(ObjectsClass *);
+		static Fn orig = next_symbol<Fn>("_ZN12ObjectsClass9femKernelEv");
+		orig(this);
+		return;
+	}
+	Timed timed(dev.t_fem);
+	fem_setup(*this);
+	// marker forces and epsilon are on the device already (the life_ibm_interp that precedes this call, src/Objects.cpp:40-47)
+	double sums[3];
+	dfem.per_body.resize(5 * dfem.body.size());
+	LIFE_CK(life_fem_dynamic(dev.ctx, sums, dfem.per_body.data()));
+	for (size_t k = 0; k < dfem.body.size(); k++) {
+		FEMBodyClass *s = dfem.body[k]->sBody;
+		s->subRes = dfem.per_body[5 * k]; s->subNum = dfem.per_body[5 * k + 1]; s->subDen = dfem.per_body[5 * k + 2];
+		s->resNR = dfem.per_body[5 * k + 3]; s->itNR = (int)dfem.per_body[5 * k + 4];
+	}
+	fem_refresh_host(*this);
+	subRes = sqrt(sums[0]) / (ref_L * sqrt(static_cast<double>(simDOFs)));      // src/Objects.cpp:95-97
+	subNum = sums[1];
+	subDen = sums[2];
+	dev.fem_calls++;
 }
 
 // ---- ObjectsClass::ibmKernelInterp ----------------------------------------------------------------------------------------------

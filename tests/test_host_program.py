@@ -77,8 +77,13 @@ def _compare(case, ref_dir, new_dir):
     return a["t"], err
 
 
+_FEM_UNRUN = pytest.mark.xfail(strict=False, reason="the femKernel / recomputeObjectVals bindings of life_host.cpp (LIFE_B200_DEVICE_FEM=1) have not "
+                                                    "run on a B200 yet; the solver itself has (tests/test_gpu_fem.py)")
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("device_eps", [0, 1, 2, 3, "host-io"], ids=["host-eps", "device-assembly+lapack", "device-eps", "auto-eps", "host-io"])
+@pytest.mark.parametrize("device_eps", [0, 1, 2, 3, "host-io", pytest.param("device-fem", marks=_FEM_UNRUN)],
+                         ids=["host-eps", "device-assembly+lapack", "device-eps", "auto-eps", "host-io", "device-fem"])
 @pytest.mark.parametrize("case", EXAMPLES)
 def test_program_reproduces_reference_results(case, device_eps, tmp_path):
     """Default build of the drop-in: device-fed files (life_write_vtk / life_write_restart / life_read_restart / life_max_speed);
@@ -90,14 +95,20 @@ def test_program_reproduces_reference_results(case, device_eps, tmp_path):
         device_eps = 0
         if case not in ("ChannelFlow", "TurekHron"):
             pytest.skip("the host-mirror I/O variant is exercised on one plain and one restarted body case")
+    device_fem = device_eps == "device-fem"
+    if device_fem:
+        device_eps = 1
+        if case not in FLEXIBLE:
+            pytest.skip("the structural solver only runs for flexible bodies")
     if device_eps and case not in FLEXIBLE:
         pytest.skip("epsilon is only recomputed for flexible bodies")
     times = 2 if case == "TurekHron" else 1          # second run restarts from Results/Restart (store-ref-data.sh:51-53)
     ref = _run(case, "LIFE_ref", str(tmp_path / "ref"), times)
     assert ref.returncode == 0, ref.stdout[-2000:]
     new = _run(case, "LIFE_b200", str(tmp_path / "b200"), times, LIFE_B200_DEVICE_EPSILON=str(device_eps),
-               LIFE_B200_HOST_IO="1" if host_io else "0")
+               LIFE_B200_HOST_IO="1" if host_io else "0", LIFE_B200_DEVICE_FEM="1" if device_fem else "0")
     assert new.returncode == 0, new.stdout[-2000:] + new.stderr[-2000:]
+    assert ("life_fem_dynamic calls" in new.stderr) == device_fem
     assert "life_step" in new.stderr and " 0 life_step" not in new.stderr      # the CUDA path really ran
     assert (" 0 life_ibm_compute_epsilon" in new.stderr) == (not device_eps)
     print("\n%s wall time of the last run (500 steps incl. all host work and I/O): LIFE_ref %.2f s (%d host threads), LIFE_b200 %.2f s   %s"

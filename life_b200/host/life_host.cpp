@@ -360,7 +360,9 @@ void fem_setup(ObjectsClass &o) {
 }
 
 // device -> host: FEM state vectors (and the geometry that follows from U), marker positions and velocities of the flexible bodies
-void fem_refresh_host(ObjectsClass &o) {
+// `geometry_from_U_km1`: after the predictor / relaxed update the displacement the geometry belongs to sits in U_km1 (the
+// reference updates the geometry first and swaps U with U_km1 afterwards, src/FEMBody.cpp:279-288, src/Objects.cpp:199-208)
+void fem_refresh_host(ObjectsClass &o, bool geometry_from_U_km1) {
 	const size_t nm = o.iNode.size();
 	dfem.pos.resize(2 * nm); dfem.vel.resize(2 * nm);
 	LIFE_CK(life_ibm_get_markers(dev.ctx, dfem.pos.data(), dfem.vel.data()));
@@ -370,7 +372,9 @@ void fem_refresh_host(ObjectsClass &o) {
 		dfem.state.resize(11 * (size_t)s->bodyDOFs);
 		LIFE_CK(life_fem_get_state(dev.ctx, (int32_t)k, dfem.state.data()));
 		for (int v = 0; v < 11; v++) std::copy(dfem.state.begin() + (size_t)v * s->bodyDOFs, dfem.state.begin() + (size_t)(v + 1) * s->bodyDOFs, fem_vector(s, v)->begin());
+		if (geometry_from_U_km1) s->U.swap(s->U_km1);
 		s->updateFEMValues();
+		if (geometry_from_U_km1) s->U.swap(s->U_km1);
 		for (size_t i = 0; i < b->node.size(); i++) {
 			const size_t g = (size_t)(b->node[i] - &o.iNode[0]);
 			b->node[i]->pos[eX] = dfem.pos[2 * g]; b->node[i]->pos[eY] = dfem.pos[2 * g + 1];
@@ -398,7 +402,7 @@ void ObjectsClass::recomputeObjectVals() {
 			else relax = -relax * subNum / subDen;
 			LIFE_CK(life_fem_relax(dev.ctx, relax));                           // src/Objects.cpp:195-208
 		}
-		fem_refresh_host(*this);
+		fem_refresh_host(*this, true);
 	}
 	// supports and ds of the moved markers, then epsilon: the reference's own host code (src/Objects.cpp:214-231)
 #pragma omp parallel for schedule(guided)
@@ -429,7 +433,7 @@ void ObjectsClass::femKernel() {
 		s->subRes = dfem.per_body[5 * k]; s->subNum = dfem.per_body[5 * k + 1]; s->subDen = dfem.per_body[5 * k + 2];
 		s->resNR = dfem.per_body[5 * k + 3]; s->itNR = (int)dfem.per_body[5 * k + 4];
 	}
-	fem_refresh_host(*this);
+	fem_refresh_host(*this, false);
 	subRes = sqrt(sums[0]) / (ref_L * sqrt(static_cast<double>(simDOFs)));      // src/Objects.cpp:95-97
 	subNum = sums[1];
 	subDen = sums[2];

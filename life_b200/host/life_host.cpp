@@ -15,7 +15,8 @@
 //                                     =2 -> life_ibm_compute_epsilon (assembly and LU both on the GPU);
 //                                     =3 -> per body: GPU LU for small systems (<= 64 markers, many of them: Honami), GPU
 //                                     assembly + host LAPACK for large ones (UNI_EPSILON: TurekHron 132, PELskin 310)
-//   ObjectsClass::recomputeObjectVals / femKernel (src/Objects.cpp:152-232, :63-98), ONLY with
+//   ObjectsClass::recomputeObjectVals / femKernel (src/Objects.cpp:152-232, :63-98), ONLY in the separate
+//                                     program LIFE_b200_fem (this file compiled with -DLIFE_B200_WITH_DEVICE_FEM) and there only with
 //                                     LIFE_B200_DEVICE_FEM=1 (off by default: the device solver has had its first B200 runs through
 //                                     the C ABI, tests/test_gpu_fem.py, but THIS binding has not run yet — DESIGN.md §10):
 //                                     predictor / relaxed update / dynamicFEM of all flexible bodies on the device
@@ -289,6 +290,7 @@ void ObjectsClass::computeEpsilon() {
 	dev.eps_solves++;
 }
 
+#ifdef LIFE_B200_WITH_DEVICE_FEM   // compiled only into LIFE_b200_fem (life_b200/host/Makefile): the default program is untouched by it
 // ---- ObjectsClass::recomputeObjectVals / femKernel (optional, LIFE_B200_DEVICE_FEM=1) ------------------------------------------------
 namespace {
 
@@ -439,6 +441,7 @@ void ObjectsClass::femKernel() {
 	subDen = sums[2];
 	dev.fem_calls++;
 }
+#endif  // LIFE_B200_WITH_DEVICE_FEM
 
 // ---- ObjectsClass::ibmKernelInterp ----------------------------------------------------------------------------------------------
 void ObjectsClass::ibmKernelInterp() {

@@ -74,7 +74,7 @@ int main(int argc, char **argv) {
 		}
 		if (t % (steps / 2 > 0 ? steps / 2 : 1) == 0) {           /* writeVTK: returns at once, the worker writes while we step */
 			snprintf(path, sizeof path, "%s/Fluid.%d.vti", out, t);
-			CK(life_write_vtk(ctx, path, 1000.0, 0.0, LIFE_IO_ASYNC));
+			CK(life_write_vtk(ctx, path, 1.0 /* rho_p, with Drho = 1 */, 0.0 /* ref_P */, LIFE_IO_ASYNC));
 		}
 	}
 	snprintf(path, sizeof path, "%s/Fluid.restart", out);

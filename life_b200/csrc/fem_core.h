@@ -341,6 +341,31 @@ FEM_FN void update_markers(const Body &b, Lane l, double *pos, double *vel, cons
 	FEM_SYNC();
 }
 
+// IBMNodeClass::computeDs, src/IBMNode.cpp:182-204, for the markers of this body: distance to the nearest OTHER marker of the same
+// body in lattice units (what scales the spread force and the epsilon matrix).  Every product and sum is rounded on its own on
+// the device as well (no FMA contraction), so ds comes out bit-identical to the reference: it feeds paths that are bit-exact.
+// pos / ds are the global marker arrays, indexed through `marker` (or directly when marker == nullptr).
+FEM_FN void compute_ds(const Body &b, Lane l, const double *pos, double Dx, double *ds, const int *marker) {
+	for (int i = l.tid; i < b.n_ibm; i += l.n) {
+		const int gi = marker ? marker[i] : i;
+		const double xi = pos[2 * gi], yi = pos[2 * gi + 1];
+		double current = 10.0;
+		for (int n = 0; n < b.n_ibm; n++) {
+			if (n == i) continue;
+			const int gn = marker ? marker[n] : n;
+			const double dx = xi - pos[2 * gn], dy = yi - pos[2 * gn + 1];
+#if defined(__CUDA_ARCH__)
+			const double mag = __ddiv_rn(sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))), Dx);
+#else
+			const double mag = sqrt(dx * dx + dy * dy) / Dx;
+#endif
+			if (mag < current) current = mag;
+		}
+		ds[gi] = current;
+	}
+	FEM_SYNC();
+}
+
 // FEMBodyClass::subResidual, src/FEMBody.cpp:244-256 -> scal[1..3] = subRes, subNum, subDen
 FEM_FN void sub_residual(const Body &b, Lane l) {
 	for (int i = l.tid; i < b.n_dof; i += l.n) {

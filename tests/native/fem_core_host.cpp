@@ -80,6 +80,8 @@ void femc_dynamic(void *p, const double *force, const double *epsilon, double *p
 	fem_dynamic(b, Lane{0, 1}, force, epsilon, pos, vel, nullptr);
 	results[0] = b.scal[1]; results[1] = b.scal[2]; results[2] = b.scal[3]; results[3] = b.scal[0]; results[4] = b.scal[4];
 }
+// ds [n_ibm] of the body's markers from their positions pos [2 * n_ibm] (body-local order), lattice spacing Dx
+void femc_compute_ds(void *p, const double *pos, double Dx, double *ds) { compute_ds(static_cast<HostBody *>(p)->b, Lane{0, 1}, pos, Dx, ds, nullptr); }
 void femc_predict(void *p, int t, double *pos, double *vel) { fem_predict(static_cast<HostBody *>(p)->b, Lane{0, 1}, t, pos, vel, nullptr); }
 void femc_relax(void *p, double relax, double *pos, double *vel) { fem_relax(static_cast<HostBody *>(p)->b, Lane{0, 1}, relax, pos, vel, nullptr); }
 

@@ -42,6 +42,7 @@ for f in (L.femc_set_state, L.femc_get_state):
 L.femc_dynamic.argtypes = [C.c_void_p] * 6
 L.femc_predict.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
 L.femc_relax.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
+L.femc_compute_ds.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
 p = lambda a: a.ctypes.data_as(C.c_void_p)
 case, steps = %(case)r, %(steps)d
 r = RefCase(case)
@@ -82,6 +83,9 @@ for step in range(steps):
                 L.femc_relax(core[fb], r.relax, p(pos), p(vel))
             ref_st = r.fem_get_state(fb, d["n_dof"])
             close(pos, m["pos"][ids], "predict/relax marker pos", d["ref_L"])
+            ds = np.zeros(d["n_ibm"])                      # computeDs of the moved markers (src/IBMNode.cpp:182-204): bit for bit
+            L.femc_compute_ds(core[fb], p(np.ascontiguousarray(m["pos"][ids])), d["Dx"], p(ds))
+            assert np.array_equal(ds, m["ds"][ids]), ("ds", float(np.abs(ds - m["ds"][ids]).max()))
             close(vel, m["vel"][ids], "predict/relax marker vel", d["ref_L"] / d["Dt"] * 1e-3, 1e-8)
             got = state(core[fb], d["n_dof"])
             for k in (0, 3, 6, 9, 10):          # U, U_n, U_km1, U_nm1, U_nm2

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define LIFE_ABI_VERSION 1
+#define LIFE_ABI_VERSION 2
 
 /* lattice-site / wall types: values of eLatType, inc/defs.h:52 */
 enum {
@@ -89,7 +89,12 @@ typedef struct life_config {
 	const void *nccl_id;       /* 128-byte ncclUniqueId shared by all ranks (life_nccl_unique_id); NULL iff nranks <= 1 */
 	int32_t kernel;            /* LIFE_KERNEL_*                                                                 */
 	int32_t tune;              /* measurement only: launch-shape / cache-hint variant of the bulk sweep, 0 = default (csrc/lbm_bulk.cu) */
-	int32_t reserved[6];
+	int32_t exact;             /* 1: the LBM step in the REFERENCE'S OPERATION ORDER without FMA contraction — BGK collision, macroscopic,
+	                              regularised / convective boundaries, the outlet mean as a serial sum in j order (src/Grid.cpp:237-299,
+	                              :387-495) — so that fields, marker forces and files equal the reference's g++ build bit for bit (the
+	                              reference's own regression protocol is `diff -r`, testing/run-tests.sh:100).  ~3x the arithmetic of the
+	                              default factored collision.  Central moments: same factored form, FMA-free (deterministic, not bitwise). */
+	int32_t reserved[5];
 } life_config;
 
 typedef struct life_ctx life_ctx;

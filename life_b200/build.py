@@ -18,6 +18,10 @@ LIB = os.path.join(HERE, "lib", "liblife_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 SOURCES = ["api.cu", "lbm_bulk.cu", "lbm_boundary.cu", "lbm_io.cu", "lbm_file.cu", "halo.cu", "ibm.cu", "ibm_eps.cu", "fem.cu", "nccl_dyn.cu"]
+# second compilation of the step kernels in the reference's operation order (cfg.exact): no FMA contraction, namespace life::exact
+EXACT_FLAGS = ["-DLIFE_EXACT", "-fmad=false"]
+VARIANTS = [(s, s.replace(".cu", ".o"), []) for s in SOURCES] + \
+           [(s, s.replace(".cu", "_exact.o"), EXACT_FLAGS) for s in ("lbm_bulk.cu", "lbm_boundary.cu")]
 
 NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 # sm_100a only (B200); -lineinfo so ncu's source page maps to these files.  The host compiler is the system g++.
@@ -37,11 +41,12 @@ def build(force=False, verbose=False, extra_flags=()):
     headers = [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith((".h", ".cuh"))]
     headers.append(os.path.join(INCLUDE, "life_b200.h"))
     jobs = []
-    for s in SOURCES:
+    me = os.path.abspath(__file__)
+    for s, o, vflags in VARIANTS:
         src = os.path.join(CSRC, s)
-        obj = os.path.join(OBJ, s.replace(".cu", ".o"))
-        if force or _newer(obj, [src] + headers):
-            jobs.append([NVCC] + NVCC_FLAGS + list(extra_flags) + ["-c", src, "-o", obj])
+        obj = os.path.join(OBJ, o)
+        if force or _newer(obj, [src, me] + headers):
+            jobs.append([NVCC] + NVCC_FLAGS + vflags + list(extra_flags) + ["-c", src, "-o", obj])
 
     def run(cmd):
         if verbose:
@@ -55,7 +60,7 @@ def build(force=False, verbose=False, extra_flags=()):
     if jobs:
         with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
             list(ex.map(run, jobs))
-    objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in SOURCES]
+    objs = [os.path.join(OBJ, o) for _, o, _ in VARIANTS]
     if force or jobs or _newer(LIB, objs):
         run([NVCC, "-shared", "-ccbin", "/usr/bin/g++", "-o", LIB] + objs + ["-ldl"])
     return LIB

@@ -12,7 +12,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "liblife_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 FLUID, WALL, VELOCITY, FREESLIP, PRESSURE, CONVECTIVE = range(6)
 BGK, CENTRAL_MOMENTS = 0, 1
 KERNEL_AUTO, KERNEL_DIRECT, KERNEL_SHUFFLE, KERNEL_TMA = 0, 1, 2, 3
@@ -50,7 +50,7 @@ class Config(C.Structure):
                 ("stream", C.c_void_p),
                 ("rank", C.c_int32), ("nranks", C.c_int32),
                 ("nccl_id", C.c_void_p),
-                ("kernel", C.c_int32), ("tune", C.c_int32), ("reserved", C.c_int32 * 6)]
+                ("kernel", C.c_int32), ("tune", C.c_int32), ("exact", C.c_int32), ("reserved", C.c_int32 * 5)]
 
     def __init__(self, **kw):
         super().__init__()

@@ -149,7 +149,9 @@ int life_create(const life_config *cfg, life_ctx **out) {
 	CK(cudaEventCreateWithFlags(&ctx->ev_edge, cudaEventDisableTiming));
 	CK(cudaEventCreateWithFlags(&ctx->ev_comm, cudaEventDisableTiming));
 
-	const size_t fbytes = sizeof(double) * 9 * (size_t)L.S;
+	// + 64 doubles: the last warp of a column loads its full 64-row span even when the column ends inside it (lbm_bulk.cu), which
+	// for tiny Ny (pitch < 64 rows) reaches past the ghost column of the last plane
+	const size_t fbytes = sizeof(double) * (9 * (size_t)L.S + 64);
 	CK(cudaMalloc(&ctx->fA, fbytes));
 	CK(cudaMalloc(&ctx->fB, fbytes));
 	CK(cudaMemsetAsync(ctx->fA, 0, fbytes, ctx->stream));
@@ -402,7 +404,10 @@ int life_step(life_ctx *ctx, int32_t t) {
 	const Layout &L = ctx->L;
 	const StepScalars sc = step_scalars(ctx, t);
 	int rc;
-	if ((rc = launch_convective_speed(ctx, sc))) return rc;
+	// cfg.exact selects the kernels compiled in the reference's operation order without FMA contraction (namespace life::exact)
+	const bool exact = ctx->cfg.exact != 0;
+	auto bulk = exact ? launch_bulk_exact : launch_bulk;
+	if ((rc = exact ? launch_convective_speed_exact(ctx, sc) : launch_convective_speed(ctx, sc))) return rc;
 
 	cudaEvent_t p0 = nullptr, p1 = nullptr;
 	if (ctx->profiling) {
@@ -419,26 +424,26 @@ int life_step(life_ctx *ctx, int32_t t) {
 
 	if (ctx->cfg.nranks <= 1) {
 		if (p0) LIFE_CUDA(ctx, cudaEventRecord(p0, ctx->stream));
-		if ((rc = launch_bulk(ctx, sc, 1, L.nxl, ctx->stream))) return rc;
+		if ((rc = bulk(ctx, sc, 1, L.nxl, ctx->stream))) return rc;
 		if (p1) LIFE_CUDA(ctx, cudaEventRecord(p1, ctx->stream));
 		if ((rc = launch_wrap_y(ctx, ctx->stream, false))) return rc;
 		if ((rc = exchange_x(ctx))) return rc;
 	} else {
 		// the two edge columns first, so their ghost columns can travel while the interior is swept
-		if ((rc = launch_bulk(ctx, sc, 1, 1, ctx->stream))) return rc;
-		if ((rc = launch_bulk(ctx, sc, L.nxl, 1, ctx->stream))) return rc;
+		if ((rc = bulk(ctx, sc, 1, 1, ctx->stream))) return rc;
+		if ((rc = bulk(ctx, sc, L.nxl, 1, ctx->stream))) return rc;
 		if ((rc = launch_wrap_y(ctx, ctx->stream, false))) return rc;   // ring corners of the ghost columns
 		LIFE_CUDA(ctx, cudaEventRecord(ctx->ev_edge, ctx->stream));
 		LIFE_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_edge, 0));
 		if ((rc = exchange_x(ctx))) return rc;
 		LIFE_CUDA(ctx, cudaEventRecord(ctx->ev_comm, ctx->comm_stream));
 		if (p0) LIFE_CUDA(ctx, cudaEventRecord(p0, ctx->stream));
-		if ((rc = launch_bulk(ctx, sc, 2, L.nxl - 2, ctx->stream))) return rc;
+		if ((rc = bulk(ctx, sc, 2, L.nxl - 2, ctx->stream))) return rc;
 		if (p1) LIFE_CUDA(ctx, cudaEventRecord(p1, ctx->stream));
 		if ((rc = launch_wrap_y(ctx, ctx->stream, true))) return rc;    // what the interior sweep pushed over the top/bottom
 		LIFE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));
 	}
-	if ((rc = launch_boundary(ctx, sc))) return rc;
+	if ((rc = exact ? launch_boundary_exact(ctx, sc) : launch_boundary(ctx, sc))) return rc;
 
 	double *tmp = ctx->fA; ctx->fA = ctx->fB; ctx->fB = tmp;
 	ctx->stored_macro_valid = false;

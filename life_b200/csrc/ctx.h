@@ -149,11 +149,14 @@ int fail(life_ctx *ctx, int code, const std::string &msg);
 // launchers (each returns a LIFE_* code) ----------------------------------------------------------------------------------
 // lbm_bulk.cu
 int launch_bulk(life_ctx *ctx, const StepScalars &sc, int64_t c_first, int64_t c_count, cudaStream_t st);
+int launch_bulk_exact(life_ctx *ctx, const StepScalars &sc, int64_t c_first, int64_t c_count, cudaStream_t st);   // cfg.exact
 // lbm_boundary.cu
 int build_boundary(life_ctx *ctx);
 int launch_convective_speed(life_ctx *ctx, const StepScalars &sc);
 int launch_wrap_y(life_ctx *ctx, cudaStream_t st, bool after_exchange);
 int launch_boundary(life_ctx *ctx, const StepScalars &sc);
+int launch_convective_speed_exact(life_ctx *ctx, const StepScalars &sc);   // cfg.exact: the same two in the reference's operation order
+int launch_boundary_exact(life_ctx *ctx, const StepScalars &sc);
 // halo.cu
 int exchange_x(life_ctx *ctx);
 // lbm_io.cu

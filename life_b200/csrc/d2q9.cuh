@@ -94,6 +94,34 @@ __device__ __forceinline__ void collide_bgk(const double (&f)[NV], double rho, d
 	}
 }
 
+// BGK in the REFERENCE'S OPERATION ORDER (cfg.exact): every direction on its own, nothing shared, nothing factored —
+//   f*_v = f_v + omega (feq_v - f_v) + (1 - omega/2) F_v                                              src/Grid.cpp:243
+//   feq_v = rho w_v (1 + 3 (cx ux + cy uy) + 4.5 (ux^2 (cx^2 - 1/3) + uy^2 (cy^2 - 1/3)) + 9 cx cy ux uy)   src/Grid.cpp:262
+//   F_v   = 3 w_v (Fx (cx - ux + cx 3 (cx ux + cy uy)) + (Fy (cy - uy + cy 3 (cx ux + cy uy))))           src/Grid.cpp:278
+// with C++'s left-to-right association of each sum and product.  Only meaningful in a translation unit compiled with
+// -fmad=false (life_b200/build.py builds lbm_bulk.cu / lbm_boundary.cu a second time that way, -DLIFE_EXACT): every
+// operation below is then one IEEE double operation, as in the reference's g++ build for baseline x86-64 (no FMA), and the
+// result is the reference's double bit for bit.  The lattice velocities are compile-time constants after unrolling; the
+// terms that vanish with them are +-0 and drop out of every sum without changing it.
+template <bool HASF>
+__device__ __forceinline__ void collide_bgk_ref(const double (&f)[NV], double rho, double ux, double uy, double Fx, double Fy,
+                                                double omega, double (&o)[NV]) {
+#pragma unroll
+	for (int v = 0; v < NV; v++) {
+		const int cx = LIFE_CX(v), cy = LIFE_CY(v);
+		const double w = LIFE_W(v);
+		const double feq = rho * w * (1.0 + 3.0 * (cx * ux + cy * uy) +
+		                              4.5 * ((ux * ux) * ((cx * cx) - 1.0 / 3.0) + (uy * uy) * ((cy * cy) - 1.0 / 3.0)) +
+		                              9.0 * cx * cy * ux * uy);
+		double r = f[v] + omega * (feq - f[v]);
+		if (HASF) {
+			const double F = 3.0 * w * (Fx * (cx - ux + cx * 3.0 * (cx * ux + cy * uy)) + (Fy * (cy - uy + cy * 3.0 * (cx * ux + cy * uy))));
+			r = r + (1.0 - 0.5 * omega) * F;
+		}
+		o[v] = r;
+	}
+}
+
 // Central-moments collision (src/Grid.cpp:106-233).
 //   pre-collision   k4Pre = sum f ((cx-ux)^2 - (cy-uy)^2),  k5Pre = sum f (cx-ux)(cy-uy)            (:113-122)
 //   post-collision  k0 = rho, k1 = Fx/2, k2 = Fy/2, k3 = 2 rho cs^2, k4 = (1-w) k4Pre, k5 = (1-w) k5Pre,

@@ -7,12 +7,18 @@
 //                                                          inc/Utils.h:137-217)
 // The boundary kernel runs after the bulk sweep (and the halo exchange) on the freshly streamed buffer; it needs the
 // *new* rho/u of up to two interior neighbours, which it recomputes from their nine populations.
+//
+// Compiled twice (life_b200/build.py): as is, and with -DLIFE_EXACT -fmad=false, which puts the convective-speed and boundary
+// kernels into namespace life::exact behind launch_convective_speed_exact / launch_boundary_exact (cfg.exact).  The expressions
+// below are written in the reference's association order, so without FMA contraction every boundary population, the outlet
+// speed (then a serial sum in j order, src/Grid.cpp:483-484) and delU are the reference's doubles bit for bit.
 #include "ctx.h"
 #include "d2q9.cuh"
 #include <cmath>
 
 namespace life {
 
+#ifndef LIFE_EXACT
 // ---------------------------------------------------------------------------------------------------------------------
 // host: type matrix of the slab, BCVec order, normals
 // ---------------------------------------------------------------------------------------------------------------------
@@ -102,6 +108,10 @@ int launch_wrap_y(life_ctx *ctx, cudaStream_t st, bool after_exchange) {
 	return LIFE_OK;
 }
 
+#else    // LIFE_EXACT
+namespace exact {
+#endif   // LIFE_EXACT
+
 // ---------------------------------------------------------------------------------------------------------------------
 // shared device helpers: macroscopics of an arbitrary node recomputed from its populations
 // ---------------------------------------------------------------------------------------------------------------------
@@ -155,8 +165,27 @@ __device__ __forceinline__ void macro_end(const double *f, const Layout &L, cons
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_convective_speed(const double *f, const double *stored, Layout L, ForceView fv,
                                                            double *delU) {
-	__shared__ double red[1024];
 	const int64_t c1 = L.nxl, c2 = L.nxl - 1, c3 = L.nxl - 2;   // local columns of i = Nx-1, Nx-2, Nx-3
+#ifdef LIFE_EXACT
+	// the reference's serial loop (src/Grid.cpp:483-487): every thread fetches its u_x, one thread adds them up in j order
+	__shared__ double s_uout;
+	for (int64_t j = threadIdx.x; j < L.Ny; j += blockDim.x) {
+		const int64_t idx = L.at(c1, j + JOFF);
+		double rho, ux, uy;
+		if (stored) ux = stored[L.S + idx];
+		else macro_end(f, L, fv, idx, rho, ux, uy);
+		delU[2 * j] = ux;                                   // staging: overwritten with delU below, after the sum has been read
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		double acc = 0.0;
+		for (int64_t j = 0; j < L.Ny; j++) acc += delU[2 * j];
+		s_uout = acc / static_cast<double>(L.Ny);
+	}
+	__syncthreads();
+	const double uOut = s_uout;
+#else
+	__shared__ double red[1024];
 	double part = 0.0;
 	for (int64_t j = threadIdx.x; j < L.Ny; j += blockDim.x) {
 		const int64_t idx = L.at(c1, j + JOFF);
@@ -172,6 +201,7 @@ __global__ void __launch_bounds__(1024) k_convective_speed(const double *f, cons
 		__syncthreads();
 	}
 	const double uOut = red[0] / (double)L.Ny;
+#endif
 	for (int64_t j = threadIdx.x; j < L.Ny; j += blockDim.x) {
 		double r, a[2], b[2], c[2];
 		const int64_t i1 = L.at(c1, j + JOFF), i2 = L.at(c2, j + JOFF), i3 = L.at(c3, j + JOFF);
@@ -199,7 +229,13 @@ static ForceView force_view(life_ctx *ctx, const double uni[2]) {
 	return fv;
 }
 
+#ifdef LIFE_EXACT
+}  // namespace exact
+using namespace exact;
+int launch_convective_speed_exact(life_ctx *ctx, const StepScalars &sc) {
+#else
 int launch_convective_speed(life_ctx *ctx, const StepScalars &sc) {
+#endif
 	if (ctx->cfg.wall_right != LIFE_CONVECTIVE || ctx->i_end != ctx->cfg.Nx) return LIFE_OK;
 	if (ctx->L.nxl < 3) return fail(ctx, LIFE_E_ARG, "convective outlet needs the last three columns on one rank");
 	ForceView fv = force_view(ctx, sc.fxy_prev);
@@ -213,6 +249,9 @@ int launch_convective_speed(life_ctx *ctx, const StepScalars &sc) {
 // ---------------------------------------------------------------------------------------------------------------------
 // boundary conditions, one thread per BCVec entry
 // ---------------------------------------------------------------------------------------------------------------------
+#ifdef LIFE_EXACT
+namespace exact {
+#endif
 struct BcArgs {
 	const BcNode *bc;
 	int64_t n;
@@ -326,7 +365,12 @@ __global__ void __launch_bounds__(128) k_boundary(const BcArgs a) {
 	}
 }
 
+#ifdef LIFE_EXACT
+}  // namespace exact
+int launch_boundary_exact(life_ctx *ctx, const StepScalars &sc) {
+#else
 int launch_boundary(life_ctx *ctx, const StepScalars &sc) {
+#endif
 	if (ctx->n_bc == 0) return LIFE_OK;
 	BcArgs a{};
 	a.bc = ctx->bc; a.n = ctx->n_bc;

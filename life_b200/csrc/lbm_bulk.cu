@@ -17,10 +17,17 @@
 //   DIRECT : one node per thread, scalar shifted stores.
 //   SHUFFLE: two nodes per thread; the six populations that move in y are re-aligned across the warp with shuffles so
 //            that all but two stores per warp and plane are 16-byte aligned vector stores.
+//
+// This file is compiled twice (life_b200/build.py): as is — the fast sweep, factored collisions, FMA contraction allowed — and with
+// -DLIFE_EXACT -fmad=false, which puts the same kernels into namespace life::exact with the collision and the start-of-step
+// macroscopics written in the reference's operation order (cfg.exact; d2q9.cuh: collide_bgk_ref) behind launch_bulk_exact.
 #include "ctx.h"
 #include "d2q9.cuh"
 
 namespace life {
+#ifdef LIFE_EXACT
+namespace exact {
+#endif
 
 struct BulkArgs {
 	const double *fin;
@@ -57,9 +64,14 @@ __device__ __forceinline__ void node_update(const BulkArgs &a, int64_t idx, cons
 		if (a.macro) {
 			rho = a.macro[idx]; ux = a.macro[a.L.S + idx]; uy = a.macro[2 * a.L.S + idx];
 		} else {
+#ifdef LIFE_EXACT
+			ux = (mx + 0.5 * (fpx + fix)) / rho;      // src/IBMNode.cpp:121-122 (== src/Grid.cpp:297-298 where force_ibm is 0)
+			uy = (my + 0.5 * (fpy + fiy)) / rho;
+#else
 			const double inv = 1.0 / rho;
 			ux = (mx + 0.5 * (fpx + fix)) * inv;
 			uy = (my + 0.5 * (fpy + fiy)) * inv;
+#endif
 		}
 		if (a.wom_field) {
 			fcx = (rho * a.Drho * a.gx + a.dpdx_cos) * a.sq / a.Dm;
@@ -74,13 +86,25 @@ __device__ __forceinline__ void node_update(const BulkArgs &a, int64_t idx, cons
 			const double fix = a.fibm[idx], fiy = a.fibm[a.L.S + idx];
 			Fux += fix; Fuy += fiy; Fcx += fix; Fcy += fiy;
 		}
+#ifdef LIFE_EXACT
+		if (MODE == M_NONE) { ux = mx / rho; uy = my / rho; }      // (sum c f + 0.5 * 0) / rho, src/Grid.cpp:297-298
+		else { ux = (mx + 0.5 * Fux) / rho; uy = (my + 0.5 * Fuy) / rho; }
+#else
 		const double inv = 1.0 / rho;
 		if (MODE == M_NONE) { ux = mx * inv; uy = my * inv; }
 		else { ux = (mx + 0.5 * Fux) * inv; uy = (my + 0.5 * Fuy) * inv; }
+#endif
 	}
 	constexpr bool HASF = MODE != M_NONE;
+#ifdef LIFE_EXACT
+	// BGK: the reference's own evaluation order, bit for bit.  Central moments: the factored form without FMA contraction
+	// (deterministic, within rounding of the reference's nine expanded polynomials, src/Grid.cpp:143-223).
+	if (COLL == COLL_CM) collide_cm<HASF>(f, sum, mx, my, rho, ux, uy, Fcx, Fcy, a.omega, o);
+	else collide_bgk_ref<HASF>(f, rho, ux, uy, Fcx, Fcy, a.omega, o);
+#else
 	if (COLL == COLL_CM) collide_cm<HASF>(f, sum, mx, my, rho, ux, uy, Fcx, Fcy, a.omega, o);
 	else collide_bgk<HASF>(f, rho, ux, uy, Fcx, Fcy, a.omega, o);
+#endif
 }
 
 // ---- DIRECT: one node per thread ------------------------------------------------------------------------------------------
@@ -164,6 +188,7 @@ __global__ void __launch_bounds__(BLOCK) k_bulk_shuffle(const BulkArgs a) {
 	}
 }
 
+#ifndef LIFE_EXACT
 // ---- TMA: persistent CTAs, populations prefetched through shared memory by bulk asynchronous copies -----------------------------
 // 2 CTAs per SM stay resident for the whole sweep and walk the (column, 512-row tile) list with stride gridDim.x.  One elected
 // thread arms an mbarrier with the tile's byte count and issues nine cp.async.bulk copies (one contiguous 4 KB run per plane:
@@ -299,13 +324,21 @@ static int launch_tma(life_ctx *ctx, BulkArgs a, int64_t c_count, cudaStream_t s
 	return LIFE_OK;
 }
 
+#endif   // !LIFE_EXACT
+
 template <int COLL, int MODE>
 static int launch_one(life_ctx *ctx, const BulkArgs &a0, int64_t c_count, cudaStream_t st) {
+#ifndef LIFE_EXACT
 	if (ctx->cfg.kernel == LIFE_KERNEL_TMA) return launch_tma<COLL, MODE>(ctx, a0, c_count, st);
+#endif
 	BulkArgs a = a0;
 	const bool staged = ctx->cfg.kernel != LIFE_KERNEL_DIRECT;   // AUTO → SHUFFLE
 	// cfg.tune (measurement only, force-free shuffle kernel): tens digit = cache hint, units digit = CTA size 1:128 2:256 3:512
+#ifdef LIFE_EXACT
+	const int tune = 0;
+#else
 	const int tune = (staged && MODE == M_NONE) ? ctx->cfg.tune : 0;
+#endif
 	const int threads = (tune % 10 == 1) ? 128 : ((tune % 10 == 3) ? 512 : 256);
 	const int64_t rows_per_block = staged ? 2 * threads : threads;
 	a.tiles = (a.L.Ny + rows_per_block - 1) / rows_per_block;
@@ -314,11 +347,13 @@ static int launch_one(life_ctx *ctx, const BulkArgs &a0, int64_t c_count, cudaSt
 	if (blocks > 0x7fffffffLL) return fail(ctx, LIFE_E_ARG, "bulk sweep: grid too large");
 	if (!staged) k_bulk_direct<COLL, MODE><<<(unsigned)blocks, threads, 0, st>>>(a);
 	else if (MODE != M_NONE || tune == 0 || tune == 2) k_bulk_shuffle<COLL, MODE><<<(unsigned)blocks, threads, 0, st>>>(a);
+#ifndef LIFE_EXACT
 	else if (tune == 1) k_bulk_shuffle<COLL, M_NONE, 128, 0><<<(unsigned)blocks, threads, 0, st>>>(a);
 	else if (tune == 3) k_bulk_shuffle<COLL, M_NONE, 512, 0><<<(unsigned)blocks, threads, 0, st>>>(a);
 	else if (tune == 11) k_bulk_shuffle<COLL, M_NONE, 128, 1><<<(unsigned)blocks, threads, 0, st>>>(a);
 	else if (tune == 12) k_bulk_shuffle<COLL, M_NONE, 256, 1><<<(unsigned)blocks, threads, 0, st>>>(a);
 	else if (tune == 13) k_bulk_shuffle<COLL, M_NONE, 512, 1><<<(unsigned)blocks, threads, 0, st>>>(a);
+#endif
 	else return fail(ctx, LIFE_E_ARG, "bulk sweep: unknown cfg.tune");
 	ctx->launches++;
 	LIFE_CUDA(ctx, cudaGetLastError());
@@ -337,7 +372,14 @@ static int launch_coll(life_ctx *ctx, const BulkArgs &a, int mode, int64_t c_cou
 }
 
 // Sweep local columns [c_first, c_first + c_count) (c = i_local + 1) from ctx->fA into ctx->fB.
-int launch_bulk(life_ctx *ctx, const StepScalars &sc, int64_t c_first, int64_t c_count, cudaStream_t st) {
+#ifdef LIFE_EXACT
+}  // namespace exact
+using namespace exact;
+int launch_bulk_exact(life_ctx *ctx,
+#else
+int launch_bulk(life_ctx *ctx,
+#endif
+                const StepScalars &sc, int64_t c_first, int64_t c_count, cudaStream_t st) {
 	BulkArgs a{};
 	a.fin = ctx->fA;
 	a.fout = ctx->fB;

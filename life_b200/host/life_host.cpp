@@ -138,6 +138,9 @@ life_config make_config(const GridClass &g) {
 	c.nranks = 1;
 	const char *k = std::getenv("LIFE_B200_KERNEL");
 	c.kernel = k ? std::atoi(k) : LIFE_KERNEL_AUTO;
+	// LIFE_B200_EXACT=1: the step in the reference's operation order (bitwise equal Results/, the reference's own `diff -r` protocol)
+	const char *x = std::getenv("LIFE_B200_EXACT");
+	c.exact = x ? std::atoi(x) : 0;
 	return c;
 }
 

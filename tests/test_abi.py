@@ -21,10 +21,11 @@ def test_header_and_binding_agree():
 
 
 def test_library_exports_every_symbol(lib_built):
+    from life_b200 import capi
     lib = C.CDLL(lib_built)
     for name in _declared():
         assert hasattr(lib, name), name
-    assert lib.life_abi_version() == 1
+    assert lib.life_abi_version() == capi.ABI_VERSION == 2
 
 
 def test_struct_layout_matches_header(lib_built):

@@ -151,6 +151,45 @@ def test_program_reproduces_reference_results(case, device_eps, tmp_path):
     assert not bad, (case, bad)
 
 
+def _diff_r(ref_dir, new_dir):
+    """testing/run-tests.sh:100 — `diff -r Results RefData/Results --exclude=Log.out`: the list of files that differ."""
+    a_root, b_root = os.path.join(ref_dir, "Results"), os.path.join(new_dir, "Results")
+    listing = lambda root: sorted(os.path.relpath(os.path.join(d, f), root) for d, _, fs in os.walk(root) for f in fs if f != "Log.out")
+    la, lb = listing(a_root), listing(b_root)
+    assert la == lb, (sorted(set(la) ^ set(lb)))
+    return [f for f in la if open(os.path.join(a_root, f), "rb").read() != open(os.path.join(b_root, f), "rb").read()], len(la)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [c for c in EXAMPLES if c != "LidDrivenCavity"])
+def test_program_in_exact_mode_is_bitwise_the_reference(case, tmp_path):
+    """The reference's own regression protocol, unrelaxed: LIFE_b200 with LIFE_B200_EXACT=1 (cfg.exact: the step in the
+    reference's operation order, kernels of namespace life::exact) against LIFE_ref — 500 steps, TurekHron twice (restart), then
+    `diff -r Results` excluding Log.out must find NO differing file: every .vti / .vtp, Fluid / IBM / FEM.restart,
+    TotalForces.out, TipPositions.out ... byte for byte, with the live FEM + Aitken sub-iteration loop in between
+    (TurekHron, InvertedFlag, Honami, PELskin).  All six cases are BGK (LidDrivenCavity is central moments, tested at 1e-10)."""
+    if not (_have(case, "LIFE_b200") and _have(case, "LIFE_ref")):
+        pytest.skip("life_b200/host/_build/%s not built (make -C life_b200/host needs /root/reference)" % case)
+    times = 2 if case == "TurekHron" else 1
+    ref = _run(case, "LIFE_ref", str(tmp_path / "ref"), times)
+    assert ref.returncode == 0, ref.stdout[-2000:]
+    new = _run(case, "LIFE_b200", str(tmp_path / "b200"), times, LIFE_B200_EXACT="1")
+    assert new.returncode == 0, new.stdout[-2000:] + new.stderr[-2000:]
+    assert "life_step" in new.stderr and " 0 life_step" not in new.stderr      # the CUDA path really ran
+    differing, n_files = _diff_r(str(tmp_path / "ref"), str(tmp_path / "b200"))
+    t_end, err = _compare(case, str(tmp_path / "ref"), str(tmp_path / "b200"))
+    print("\n%s exact mode: %d files compared, differing: %s; field differences %s" % (case, n_files, differing, err))
+    assert t_end == 500 * times
+    assert not differing, (case, differing, err)
+    a = R.read_fluid(str(tmp_path / "ref" / "Results" / "Restart" / "Fluid.restart"))
+    b = R.read_fluid(str(tmp_path / "b200" / "Results" / "Restart" / "Fluid.restart"))
+    for name in ("rho", "u", "f", "force_ibm"):
+        assert np.array_equal(a[name], b[name]), (case, name)
+    # the numbers writeInfo prints (max velocity from life_max_speed) are the same text
+    for pat in (r"Max Velocity = (\S+)", r"Max Velocity \(m/s\) = (\S+)", r"Max Reynolds number = (\S+)"):
+        assert re.findall(pat, new.stdout) == re.findall(pat, ref.stdout), pat
+
+
 def test_program_refuses_to_run_without_a_gpu(tmp_path):
     """No CPU fallback: without a CUDA device the drop-in program stops through the reference's ERROR() (exit 99)."""
     import torch

@@ -26,7 +26,6 @@ def test_example_builds_and_refuses_to_run_without_a_gpu(cavity_exe, tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="the example program has not run on a B200 yet (it only strings together entry points that have)")
 def test_example_runs_and_writes_the_reference_formats(cavity_exe, tmp_path):
     from oracle import fluidfiles as F
     N, steps = 257, 40

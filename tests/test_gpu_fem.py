@@ -1,11 +1,7 @@
 """First device run of the structural solver (life_fem_* of include/life_b200.h; csrc/fem.cu over csrc/fem_core.h; SURVEY.md §8f
 row 3).  The solver's arithmetic and barrier placement are verified on the CPU (tests/test_fem_core.py) and it is compiled into
-the library.  It was written after this round's GPU budget had been spent; the last seconds of that budget went into two short
-first runs on a B200 (profiles/r01_fem_first_device_runs.txt: InvertedFlag, 6 steps, and Honami, 128 filaments, 1 step — both
-agree with the reference to rounding).  Those two cases are ordinary tests here; TurekHron and PELskin have not run on a device
-yet and are marked xfail(strict=False) until they have — an XPASS in the driver's round-end run is their confirmation, a failure
-is information for the next round, and neither takes the suite down.  Each case runs in a subprocess so that a fault cannot
-poison the CUDA context of the other tests.
+the library.  All four flexible examples have run on a B200 (round 1's round-end run, GPUTEST_r01.json) and are ordinary tests.
+Each case runs in a subprocess so that a fault cannot poison the CUDA context of the other tests.
 
 Method = tests/test_fem_core.py with the device in place of the serial host build: inside live fluid-structure runs of the
 compiled reference, every predictor / relaxed update / dynamicFEM call of every flexible body is repeated through the C ABI from
@@ -120,9 +116,8 @@ ctx.close(); r.close()
 print("OK")
 '''
 
-_unrun = pytest.mark.xfail(strict=False, reason="this case has not run on a B200 yet (GPU budget of the round; see the module docstring)")
 CASES = [pytest.param("InvertedFlag", 25, id="InvertedFlag"), pytest.param("Honami", 6, id="Honami"),
-         pytest.param("TurekHron", 40, id="TurekHron", marks=_unrun), pytest.param("PELskin", 12, id="PELskin", marks=_unrun)]
+         pytest.param("TurekHron", 40, id="TurekHron"), pytest.param("PELskin", 12, id="PELskin")]
 
 
 @pytest.mark.parametrize("case,steps", CASES)

@@ -20,8 +20,11 @@ One JSON line on stdout (rank 0):
   roofline  dominant kernel (bulk stream+collide sweep): 144 algorithmic bytes per node (9 populations x 8 B read and
             written) x nodes per launch / its average CUDA-event duration inside the timed region, against the measured
             HBM copy bandwidth of MEASURED_PEAKS.json
-  cpu_baseline  the unmodified reference (oracle/_ref/libref_syn_<coll>.so, compiled from /root/reference by
-            oracle/Makefile) timed on this box's host cores, rank 0, N = 1 only, on a bounded sample
+  cpu_baseline  the unmodified reference (oracle/_ref/libref_syn_<coll>[_8192].so, compiled from /root/reference by
+            oracle/Makefile) timed on this box's host cores by rank 0 at EVERY N (after the other ranks have finished), on bounded
+            8192^2 and 4096^2 samples, in a child process with OMP_NUM_THREADS set explicitly; the thread count is the one the
+            reference's own counter observed
+  parity_check  untimed: small cases cut into the same N slabs, compared with the committed fixtures of the compiled reference
 
 --impl reference times only that CPU reference (all host threads) and prints the same line shape.
 
@@ -60,45 +63,78 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def time_reference(collision, steps, warmup, budget_s):
-    """MLUPS of the reference's own GridClass::solver() on a SYN_N^2 sample of the synthetic cavity, all host threads.
-
-    Returns (mlups, ms_per_step, steps_timed, kind, cores, sample).  `steps` = None: as many steps as fit `budget_s`.
-    """
-    cores = host_cores()
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
-    case = "syn_cm" if collision == "cm" else "syn_bgk"
+def _ref_worker(case, steps, warmup, budget_s, threads):
+    """Child process of time_reference: loads ONE compiled-reference case (or the C restatement), times it, prints one JSON line."""
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
     from oracle import refharness
+    collision = "cm" if "_cm" in case else "bgk"
     if refharness.available(case):
         ref = refharness.RefCase(case)
-        n = ref.Nx * ref.Ny
-        kind = "reference"
-        sample = ("unmodified reference GridClass::solver() compiled from /root/reference (oracle/_ref/libref_%s.so), "
-                  "%dx%d cavity (the reference's 32-bit indices cap it below 15447^2), OpenMP x%d"
-                  % (case, ref.Nx, ref.Ny, cores))
-        step = ref.step
+        ref.lib.ref_set_omp_threads(int(threads))         # libgomp may have read an inherited OMP_NUM_THREADS=1 already
+        observed = int(ref.lib.ref_omp_threads())         # the reference's own Utils::omp_thread_count (src/Utils.cpp:228-240)
+        Nx, Ny, kind = ref.Nx, ref.Ny, "reference"
+        what = "unmodified reference GridClass::solver() compiled from /root/reference (oracle/_ref/libref_%s.so)" % case
     else:
         # the compiled reference did not travel: time the C restatement instead (same loops, OpenMP)
         from oracle import oracle as O
-        N = REF_SAMPLE_N
+        N = 8192 if case.endswith("_8192") else REF_SAMPLE_N
         p = O.Params(Nx=N, Ny=N, omega=1.0, wall_top=O.VELOCITY, central_moments=int(collision == "cm"),
                      nu_p=(1.0 / 6.0) / (0.1 * (N - 1)))
         ref = O.Oracle(p)
-        n = N * N
-        kind = "port"
-        sample = "oracle/life_oracle.c restatement, %dx%d cavity, OpenMP x%d" % (N, N, cores)
-        step = ref.step
+        Nx, Ny, kind, observed = N, N, "port", int(threads)
+        what = "oracle/life_oracle.c restatement"
     t0 = time.perf_counter()
-    step(max(1, warmup))
+    ref.step(max(1, warmup))
     per = (time.perf_counter() - t0) / max(1, warmup)
-    if steps is None:
+    if steps <= 0:
         steps = max(3, min(200, int(budget_s / max(per, 1e-6))))
     t0 = time.perf_counter()
-    step(steps)
+    ref.step(steps)
     dt = time.perf_counter() - t0
     ref.close()
-    return n * steps / dt / 1e6, dt / steps * 1e3, steps, kind, cores, sample
+    print(json.dumps({"mlups": Nx * Ny * steps / dt / 1e6, "ms_per_step": dt / steps * 1e3, "steps": steps, "kind": kind,
+                      "threads": observed, "Nx": Nx, "Ny": Ny, "what": what}), flush=True)
+    return 0
+
+
+def time_reference(collision, steps, warmup, budget_s, size=REF_SAMPLE_N):
+    """MLUPS of the reference's own GridClass::solver() on a size^2 sample of the synthetic cavity (4096 or 8192: the cases
+    oracle/Makefile compiles), on every host core this process may use.
+
+    Runs in a CHILD process whose OMP_NUM_THREADS is set explicitly: under torch.distributed.run the parent inherits
+    OMP_NUM_THREADS=1, and libgomp in a process that has imported torch has read it already.  The child reports the team size
+    the reference's own thread counter observed.  Returns a dict (mlups, ms_per_step, steps, kind, threads, Nx, Ny, sample).
+    """
+    cores = host_cores()
+    case = ("syn_cm" if collision == "cm" else "syn_bgk") + ("_8192" if size == 8192 else "")
+    env = dict(os.environ, OMP_NUM_THREADS=str(cores), OPENBLAS_NUM_THREADS="1")
+    for k in ("OMP_PROC_BIND", "OMP_PLACES", "GOMP_CPU_AFFINITY"):
+        env.pop(k, None)
+    cmd = [sys.executable, os.path.abspath(__file__), "--ref-worker", case, str(steps or 0), str(warmup), str(budget_s), str(cores)]
+    p = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+    if p.returncode != 0:
+        raise RuntimeError("reference worker failed: " + p.stderr[-500:])
+    r = json.loads(p.stdout.strip().splitlines()[-1])
+    r["cores"] = cores
+    r["sample"] = ("%s, %dx%d lid-driven cavity (the reference's 32-bit indices cap it below 15447^2), OpenMP threads observed %d "
+                   "of %d host cores, %d steps, %.0f ms/step" % (r["what"], r["Nx"], r["Ny"], r["threads"], cores, r["steps"], r["ms_per_step"]))
+    return r
+
+
+def cpu_baseline_block(collision, budget_s=12.0):
+    """cpu_baseline of the JSON line: the 8192^2 sample is the value, the 4096^2 sample is listed beside it."""
+    out = {"value": None, "unit": UNIT, "cores": host_cores(), "kind": "reference", "sample": None, "samples": []}
+    try:
+        for size, budget in ((8192, budget_s), (REF_SAMPLE_N, budget_s / 2)):
+            r = time_reference(collision, None, 1, budget, size)
+            out["samples"].append({"lattice": "%dx%d" % (r["Nx"], r["Ny"]), "value": r["mlups"], "steps": r["steps"],
+                                   "ms_per_step": r["ms_per_step"], "threads": r["threads"], "kind": r["kind"]})
+            if out["value"] is None:
+                out.update(value=r["mlups"], kind=r["kind"], sample=r["sample"], cores=r["threads"])
+    except Exception as ex:   # the checker must never take the measurement down
+        out["sample"] = "failed: %r" % (ex,)
+    return out
 
 
 def run_reference_arm(args):
@@ -107,17 +143,28 @@ def run_reference_arm(args):
         return 0
     # bounded: the whole run (warm-up included) stays within a few minutes whatever K is asked for
     t0 = time.perf_counter()
-    mlups, ms, steps, kind, cores, sample = time_reference(args.collision, None if args.steps is None else min(args.steps, 400),
-                                                           min(args.warmup, 5), 20.0)
-    log("reference arm: %.1f MLUPS, %d steps, %.1f s" % (mlups, steps, time.perf_counter() - t0))
-    S = args.size
+    W = min(args.warmup, 3)
+    K = None if args.steps is None else min(args.steps, 60)
+    big = time_reference(args.collision, K, W, 20.0, 8192)
+    small = time_reference(args.collision, None if K is None else min(4 * K, 200), W, 8.0, REF_SAMPLE_N)
+    log("reference arm: %.1f MLUPS at 8192^2 (%d steps), %.1f MLUPS at 4096^2, %d OpenMP threads, %.1f s"
+        % (big["mlups"], big["steps"], small["mlups"], big["threads"], time.perf_counter() - t0))
+    cfg = workload_config(args.size, args.gpus, args.collision)
+    cfg["workload"] = ("CPU SAMPLE of BASELINE.json configs[4]: the synthetic lid-driven cavity at %dx%d (not %dx%d: the reference's "
+                       "32-bit indices overflow at 15447^2 and it needs 228 B/node of host RAM), same walls / omega / lid speed; MLUPS is "
+                       "size-normalised" % (big["Nx"], big["Ny"], cfg["Nx"], cfg["Ny"]))
+    cfg.update(Nx=big["Nx"], Ny=big["Ny"], parallelism="OpenMP x%d, one process" % big["threads"], gpu_arm_lattice="%dx%d" % (args.size * args.gpus, args.size))
+    cfg.pop("l2", None)
+    samples = [{"lattice": "%dx%d" % (r["Nx"], r["Ny"]), "value": r["mlups"], "steps": r["steps"], "ms_per_step": r["ms_per_step"],
+                "threads": r["threads"], "kind": r["kind"]} for r in (big, small)]
     line = {
-        "impl": "reference", "metric": METRIC, "value": mlups, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": min(args.warmup, 5), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": big["mlups"], "unit": UNIT, "n_gpus": args.gpus, "steps": big["steps"],
+        "warmup": W, "ms_per_step": big["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(S, args.gpus, args.collision),
-        "cpu_baseline": {"value": mlups, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
-        "e2e": {"value": mlups, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": cfg,
+        "cpu_baseline": {"value": big["mlups"], "unit": UNIT, "cores": big["threads"], "kind": big["kind"], "sample": big["sample"],
+                         "samples": samples},
+        "e2e": {"value": big["mlups"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
@@ -208,6 +255,74 @@ def unpin(torch, a):
         torch.cuda.cudart().cudaHostUnregister(a.ctypes.data)
     except Exception:
         pass
+
+
+def parity_spot_check(capi, D, dist, rank, world, local, dev):
+    """Untimed slab-parity check on the SAME ranks / communicator layout as the benchmark (the driver's test box has one GPU, so
+    the multi-GPU path would otherwise only be exercised by the timing): small cases cut into `world` slabs, every rank's slab
+    compared with the COMMITTED FIXTURES the compiled reference wrote (tests/golden/*.npz: sampled fields, marker forces of the
+    recorded FSI trace) — no oracle involved.
+      t_periodic_cm   fast kernels, central moments, periodic ring        rho, u, f at the sampled nodes <= 1e-10
+      t_periodic_bgk, t_womersley, t_convective   cfg.exact              the reference's doubles, bit for bit
+      Cylinder, Honami  (bodies; supports straddle the slab faces)       trace forces and sampled fields <= 1e-10
+    Returns the dict that goes into the JSON line as "parity_check"."""
+    import numpy as np
+    import torch
+    from tests import fixture_state as FS
+
+    def rel(a, b, floor=0.0):
+        a, b = np.asarray(a, float).ravel(), np.asarray(b, float).ravel()
+        n = max(np.linalg.norm(b), floor * np.sqrt(max(b.size, 1)))
+        return float(np.linalg.norm(a - b) / n) if n > 0 else float(np.linalg.norm(a - b))
+
+    out, ok_all = {}, True
+    plan = [("t_periodic_cm", 0), ("t_periodic_bgk", 1), ("t_womersley", 1), ("t_convective", 1), ("Cylinder", 0), ("Honami", 0)]
+    for case, exact in plan:
+        g = FS.load(case)
+        Nx = int(g["Nx"])
+        if Nx // world < 4:
+            out[case] = "skipped (slabs thinner than 4 columns)"
+            continue
+        f, rho, u, fxy, u_in, rho_in = FS.initial_state(g)
+        cfg = capi.Config(device=local, rank=rank, nranks=world, exact=exact, **FS.config_kwargs(g))
+        ctx = capi.Context(cfg, nccl_id=D.share_nccl_id() if world > 1 else None)
+        b, e = ctx.i_begin, ctx.i_end
+        ctx.upload_state(f[b:e], rho[b:e], u[b:e], fxy[b:e], None, u_in, rho_in)
+        worst = 0.0
+        steps = int(g["steps"])
+        if "trace_step" in g.files:
+            k = 0
+            for t in range(1, steps + 1):
+                ctx.step(t)
+                while True:
+                    ctx.ibm_set_markers(g["trace_pos"][k], g["trace_vel"][k], g["trace_ds"][k], g["trace_eps"][k])
+                    worst = max(worst, rel(ctx.ibm_interp(), g["trace_force"][k], 1e-6))
+                    k += 1
+                    if g["trace_last"][k - 1]:
+                        break
+                ctx.ibm_spread()
+        else:
+            ctx.step_n(1, steps)
+        st = ctx.download_state()
+        ctx.close()
+        m, il, j = FS.sample_index(g, b, e)
+        bitwise = True
+        for name in ("rho", "u", "f") + (("force_ibm",) if "trace_step" in g.files else ()):
+            if m.any():
+                got, want = st[name][il, j], g[name][m]
+                worst = max(worst, rel(got, want, 1e-12 if name == "force_ibm" else (1e-5 if name == "u" else 0.0)))
+                bitwise = bitwise and bool(np.array_equal(got, want))
+        ok = (bitwise if exact else worst < 1e-10)
+        flag = torch.tensor([0.0 if ok else 1.0, worst], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        ok, worst = flag[0].item() == 0.0, float(flag[1].item())
+        out[case] = {"slabs": world, "steps": steps, "mode": "exact: bitwise" if exact else "fast: rel L2 <= 1e-10",
+                     "worst_rel_l2": worst, "ok": ok}
+        ok_all = ok_all and ok
+    out["ok"] = ok_all
+    out["against"] = "tests/golden/*.npz written by the compiled reference (oracle/_ref), sampled nodes of every rank's slab + FSI trace forces"
+    return out
 
 
 def run_gpu_arm(args):
@@ -375,6 +490,16 @@ def run_gpu_arm(args):
         unpin(torch, a)
     del h_f, h_rho, h_u
 
+    # ---- untimed: slab parity on this very rank layout ---------------------------------------------------------------------
+    parity = None
+    if not args.no_parity_check:
+        try:
+            parity = parity_spot_check(capi, D, dist, rank, world, local, dev)
+        except Exception as ex:
+            parity = {"ok": False, "error": repr(ex)}
+        if rank == 0:
+            log("parity spot check on %d slab(s): %s" % (world, "ok" if parity.get("ok") else "FAILED %r" % (parity,)))
+
     # ---- report ------------------------------------------------------------------------------------------------------------
     peaks, peak_src = None, "fallback (B200_PROFILING.md)"
     try:
@@ -384,36 +509,32 @@ def run_gpu_arm(args):
     except Exception:
         peak = 6650.0
     achieved = BYTES_PER_NODE * bulk_nodes / (bulk_ms * 1e-3) / 1e9 if bulk_ms > 0 else None
-    traffic = None
+    traffic, traffic_src = None, "none for this configuration"
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         key = "%s_%d" % (args.collision, S)
         if key in tr and world == 1:
             traffic = tr[key]["dram_bytes_per_launch"]
+            traffic_src = "static: ncu --set full capture of this kernel on this workload, %s (profiles/traffic.json); not measured in this run" % tr[key].get("source", "profiles/")
     except Exception:
         pass
-
-    cpu = None
-    if world == 1 and rank == 0 and not args.no_cpu_baseline:
-        try:
-            mlups, ms, steps, kind, cores, sample = time_reference(args.collision, None, 2, 15.0)
-            cpu = {"value": mlups, "unit": UNIT, "cores": cores, "kind": kind,
-                   "sample": sample + ", %d steps, %.0f ms/step" % (steps, ms)}
-        except Exception as ex:   # the checker must never take the measurement down
-            cpu = {"value": None, "unit": UNIT, "cores": host_cores(), "kind": "reference", "sample": "failed: %r" % (ex,)}
 
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if rank != 0:
         return 0
+    # the reference's OpenMP build on this box's host cores, beside the GPU number at EVERY N (rank 0 alone, after the other
+    # ranks have finished: they exit while this runs, so the sample has the host to itself)
+    torch.cuda.empty_cache()
+    cpu = None if args.no_cpu_baseline else cpu_baseline_block(args.collision)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong" if args.global_nx > 0 else "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": dict(workload_config(S, world, args.collision), Nx=Nx, **({"workload": "synthetic lid-driven cavity, global lattice %dx%d cut into %d x-slabs (strong scaling)" % (Nx, Ny, world)} if args.global_nx > 0 else {})),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                     "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src,
                      "kernel": "k_bulk (fused stream+collide sweep)", "kernel_ms": bulk_ms, "launches_timed": bulk_n,
                      "nodes_per_launch": bulk_nodes, "peak_source": peak_src,
                      "step_frac": (BYTES_PER_NODE * nodes_local / (ms_total / K * 1e-3) / 1e9) / peak},
@@ -425,6 +546,7 @@ def run_gpu_arm(args):
                         "life_download_macro(pinned host rho,u); per-rank bytes averaged over the steps" % (K, tinfo)},
         "gpu_launches": launches,
         "clocks": clocks,
+        "parity_check": parity,
     }
     print(json.dumps(line), flush=True)
     return 0
@@ -442,10 +564,15 @@ def main():
     ap.add_argument("--global-nx", type=int, default=0,
                     help="strong scaling: fix the global lattice at GLOBAL_NX x SIZE and cut it into --gpus slabs (default: weak scaling, SIZE x SIZE per GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--ref-worker", nargs=5, default=None, help=argparse.SUPPRESS)
     ap.add_argument("--host-chunk-columns", type=int, default=0,
                     help="stream the host image through life_upload_columns / life_download_columns in ranges of this many "
                          "columns (0 = whole slab if host RAM allows, else automatic)")
     args = ap.parse_args()
+    if args.ref_worker:
+        case, steps, warmup, budget, threads = args.ref_worker
+        return _ref_worker(case, int(steps), int(warmup), float(budget), int(threads))
     if args.impl == "reference":
         return run_reference_arm(args)
     if args.steps is None:

@@ -100,6 +100,11 @@ REF_API int ref_profile() {
 }
 
 // ---- time loop pieces ----------------------------------------------------------------------------------------------
+// OpenMP team size: what the reference's own counter observes in a parallel region (src/Utils.cpp:228-240), and a setter so a
+// harness can undo an inherited OMP_NUM_THREADS=1 (torch.distributed.run exports that to every worker)
+REF_API int ref_omp_threads() { return Utils::omp_thread_count(); }
+REF_API void ref_set_omp_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+
 REF_API int ref_get_t() { return g_grid->t; }
 REF_API void ref_set_t(int t) { g_grid->t = t; }
 

@@ -1,0 +1,86 @@
+"""Parity at the SCALE of the headline workload ("parity spot-check of the same synthetic at 1024^2-4096^2 for
+N = 100 steps against the oracle before timing"): BASELINE.json configs[4], the synthetic lid-driven cavity bench.py times,
+  * at 4096^2 for 100 steps against the UNMODIFIED REFERENCE compiled for exactly that case (oracle/_ref/libref_syn_bgk.so /
+    libref_syn_cm.so — the same shared objects bench.py's cpu_baseline leg times), whole fields: rho, u, f <= 1e-10 with the
+    default kernels, and bit for bit in exact mode (BGK);
+  * at 8192^2 for 20 steps against the 64-bit C oracle (oracle/life_oracle.c), whole fields <= 1e-10.
+16384^2 itself is beyond the reference (its int indices overflow at 15447^2); there the size-independent
+properties of tests/test_gpu_lbm.py (conservation, mirror symmetry) apply.
+"""
+import numpy as np
+import pytest
+
+from tests import cases as K
+
+pytestmark = pytest.mark.gpu
+
+
+def _cavity_config(capi, N, collision, **kw):
+    # the reference's scalings for this case (src/Grid.cpp:1257-1260 with height_p = 1, omega = 1, lid 0.1 lattice units)
+    Dx = 1.0 / (N - 1)
+    nu_p = (1.0 / 6.0) / (0.1 * (N - 1))
+    return capi.Config(Nx=N, Ny=N, omega=1.0, collision=collision, wall_top=capi.VELOCITY, Dx=Dx, Dm=Dx ** 3,
+                       Dt=(1.0 / np.sqrt(3.0)) ** 2 * Dx * Dx * 0.5 / nu_p, **kw)
+
+
+@pytest.mark.parametrize("collision,exact", [("bgk", 0), ("bgk", 1), ("cm", 0)], ids=["bgk-fast", "bgk-exact", "cm-fast"])
+def test_cavity_4096_against_the_compiled_reference(collision, exact):
+    from life_b200 import capi
+    from oracle import refharness as RH
+    case = "syn_cm" if collision == "cm" else "syn_bgk"
+    if not RH.available(case):
+        pytest.skip("oracle/_ref/libref_%s.so not built" % case)
+    ref = RH.RefCase(case)
+    try:
+        N = ref.Nx
+        assert N == ref.Ny == 4096
+        cfg = _cavity_config(capi, N, capi.CENTRAL_MOMENTS if collision == "cm" else capi.BGK, exact=exact)
+        # the configuration bench.py uses must be the reference's own (same doubles)
+        assert (cfg.Dx, cfg.Dt, cfg.Dm, cfg.omega) == (ref.Dx, ref.Dt, ref.Dm, ref.omega)
+        ctx = capi.Context(cfg)
+        ctx.upload_state(ref.f(), ref.rho(), ref.u(), ref.force_xy(), None, ref.u_in(), ref.rho_in())
+        steps = 100
+        ctx.step_n(1, steps)
+        ref.step(steps)
+        st = ctx.download_state()
+        ctx.close()
+        for name, want in (("rho", ref.rho()), ("u", ref.u()), ("f", ref.f())):
+            if exact:
+                assert np.array_equal(st[name], want), (name, K.rel_l2(st[name], want))
+            else:
+                err = K.rel_l2(st[name], want)
+                assert err < K.TOL, (collision, name, err)
+            del want
+        assert 0.05 < np.abs(st["u"]).max() <= 0.1 + 1e-12     # the lid has set the fluid in motion
+    finally:
+        ref.close()
+
+
+def test_cavity_8192_against_the_64bit_oracle():
+    from life_b200 import capi
+    from oracle import oracle as O
+    N, steps = 8192, 20
+    p = O.Params(Nx=N, Ny=N, omega=1.0, wall_top=O.VELOCITY, nu_p=(1.0 / 6.0) / (0.1 * (N - 1)))
+    o = O.Oracle(p)
+    cfg = _cavity_config(capi, N, capi.BGK)
+    assert (cfg.Dx, cfg.Dt, cfg.Dm) == (o.Dx, o.Dt, o.Dm)
+    ctx = capi.Context(cfg)
+    ctx.upload_state(o.view("f"), o.view("rho"), o.view("u"), None, None, o.view("u_in"), o.view("rho_in"))
+    ctx.step_n(1, steps)
+    o.step(steps)
+    # compare in column ranges so the host never holds two whole 4.8 GB images
+    C = 512
+    num = {k: 0.0 for k in ("rho", "u", "f")}
+    den = dict(num)
+    buf = {"f": np.empty((C, N, 9)), "rho": np.empty((C, N)), "u": np.empty((C, N, 2))}
+    for il0 in range(0, N, C):
+        ctx.download_columns_into(il0, C, buf["f"], buf["rho"], buf["u"], None)
+        for k in num:
+            want = o.view(k)[il0:il0 + C]
+            num[k] += float(((buf[k] - want) ** 2).sum())
+            den[k] += float((want ** 2).sum())
+    ctx.close()
+    o.close()
+    for k in num:
+        err = np.sqrt(num[k] / den[k])
+        assert err < K.TOL, (k, err)

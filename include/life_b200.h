@@ -64,7 +64,8 @@ enum {
 	LIFE_KERNEL_AUTO = 0,
 	LIFE_KERNEL_DIRECT = 1,   /* one node per thread, shifted scalar stores                                          */
 	LIFE_KERNEL_SHUFFLE = 2,  /* two nodes per thread, 16-byte loads, y-moving populations re-aligned with warp shuffles */
-	LIFE_KERNEL_TMA = 3       /* persistent CTAs, column tiles moved by bulk async copies through shared memory      */
+	LIFE_KERNEL_TMA = 3,      /* persistent CTAs, column tiles moved by bulk async copies through shared memory      */
+	LIFE_KERNEL_QUAD = 4      /* four nodes per thread, 32-byte LDG.256 / STG.256 (needs Ny % 128 == 0, else SHUFFLE) */
 };
 
 /*
@@ -355,6 +356,13 @@ int life_bulk_kernel_ms(life_ctx *ctx, double *avg_ms, int64_t *launches);
 
 /* Enable (1) / disable (0) the per-launch event timing read by life_bulk_kernel_ms. */
 int life_set_profiling(life_ctx *ctx, int32_t on);
+
+/* What the memory system of `device` (-1: current) delivers to plain streaming kernels, best of `iters` launches over `bytes`
+ * (csrc/membw.cu): mode 0 read only, 1 write only, 2 copy with 16-byte LDG/STG, 3 copy with 32-byte LDG/STG, 4 copy through TMA
+ * bulk copies (global -> shared -> global), 5 / 6 copy of 9 planes into 9 planes with 16- / 32-byte accesses (the sweep's address
+ * pattern and launch shape without its arithmetic).
+ * GB/s of bytes read + written.  The ceiling the sweep's achieved bandwidth is put next to; not on the product path. */
+int life_membw(int32_t device, int32_t mode, int64_t bytes, int32_t iters, double *gbytes_per_s);
 
 #ifdef __cplusplus
 }

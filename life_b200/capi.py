@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, "lib", "liblife_b200.so")
 ABI_VERSION = 2
 FLUID, WALL, VELOCITY, FREESLIP, PRESSURE, CONVECTIVE = range(6)
 BGK, CENTRAL_MOMENTS = 0, 1
-KERNEL_AUTO, KERNEL_DIRECT, KERNEL_SHUFFLE, KERNEL_TMA = 0, 1, 2, 3
+KERNEL_AUTO, KERNEL_DIRECT, KERNEL_SHUFFLE, KERNEL_TMA, KERNEL_QUAD = 0, 1, 2, 3, 4
 OK, E_ARG, E_CUDA, E_NCCL, E_STATE, E_SUPPORT, E_NOMEM, E_IO = range(8)
 IO_SYNC, IO_ASYNC = 0, 1
 
@@ -27,7 +27,7 @@ EXPORTS = [
     "life_download_macro", "life_download_state", "life_max_speed", "life_step", "life_step_n",
     "life_sync", "life_ibm_set_markers", "life_ibm_interp", "life_ibm_spread", "life_ibm_compute_epsilon", "life_ibm_assemble_epsilon", "life_ibm_set_forces",
     "life_ibm_get_interp", "life_ibm_get_supports", "life_get_boundary", "life_get_types", "life_launch_count",
-    "life_bulk_kernel_ms", "life_set_profiling",
+    "life_bulk_kernel_ms", "life_set_profiling", "life_membw",
     "life_vtk_frame", "life_write_vtk", "life_write_restart", "life_io_wait", "life_io_busy", "life_io_stats", "life_io_set_staging",
     "life_read_restart",
     "life_fem_create", "life_fem_set_state", "life_fem_get_state", "life_fem_predict", "life_fem_relax", "life_fem_dynamic",
@@ -145,6 +145,17 @@ def load():
     L.life_ibm_get_markers.argtypes = [vp, vp, vp]
     _lib = L
     return L
+
+
+def membw(mode, nbytes=8 << 30, iters=5, device=-1):
+    """GB/s of the library's plain streaming kernels (life_membw): the memory-system ceiling next to the sweep's number."""
+    L = load()
+    L.life_membw.argtypes = [C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.POINTER(C.c_double)]
+    out = C.c_double(0.0)
+    rc = L.life_membw(int(device), int(mode), int(nbytes), int(iters), C.byref(out))
+    if rc != OK:
+        raise LifeError(rc, "life_membw(mode=%d)" % mode)
+    return out.value
 
 
 def nccl_unique_id():

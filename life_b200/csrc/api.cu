@@ -51,7 +51,7 @@ static void free_ctx(life_ctx *ctx) {
 	fem_free(ctx);
 	ibm_free(ctx);
 	if (ctx->comm) ncclCommDestroy(ctx->comm);
-	cudaFree(ctx->fA); cudaFree(ctx->fB); cudaFree(ctx->macro); cudaFree(ctx->fibm); cudaFree(ctx->fxyf);
+	cudaFree(ctx->fA); cudaFree(ctx->fB); cudaFree(ctx->macro); cudaFree(ctx->fibm); cudaFree(ctx->fibm_mask); cudaFree(ctx->fxyf);
 	cudaFree(ctx->cell_head); cudaFree(ctx->u_in); cudaFree(ctx->rho_in); cudaFree(ctx->delU); cudaFree(ctx->bc);
 	cudaFree(ctx->scratch); cudaFree(ctx->d_red); cudaFree(ctx->eps_buf);
 	if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
@@ -226,7 +226,10 @@ int life_upload_begin(life_ctx *ctx, const double *u_in, const double *rho_in) {
 	ctx->fibm_sites_dirty = false;
 	ctx->fibm_full_dirty = false;
 	ctx->fibm_consumed = true;
-	if (ctx->fibm) LIFE_CUDA(ctx, cudaMemsetAsync(ctx->fibm, 0, sizeof(double) * 2 * L.S, ctx->stream));
+	if (ctx->fibm) {
+		LIFE_CUDA(ctx, cudaMemsetAsync(ctx->fibm, 0, sizeof(double) * 2 * L.S, ctx->stream));
+		LIFE_CUDA(ctx, cudaMemsetAsync(ctx->fibm_mask, 0, (size_t)(ctx->mask_pitch * (L.nxl + 2)), ctx->stream));
+	}
 	if (ctx->wom_field) {   // force_xy is a field the sweep recomputes every step (src/Grid.cpp:55-61)
 		if (!ctx->fxyf) LIFE_CUDA(ctx, cudaMalloc(&ctx->fxyf, sizeof(double) * 2 * L.S));
 		LIFE_CUDA(ctx, cudaMemsetAsync(ctx->fxyf, 0, sizeof(double) * 2 * L.S, ctx->stream));

@@ -85,6 +85,9 @@ struct life_ctx {
 	double *fA = nullptr, *fB = nullptr;  // population buffers, 9 planes each; fA holds the current state
 	double *macro = nullptr;              // rho, ux, uy planes (3*S), lazily allocated
 	double *fibm = nullptr;               // force_ibm planes (2*S), lazily allocated
+	uint8_t *fibm_mask = nullptr;         // one byte per (column, 64-row span): 1 where a spread has written force_ibm.  Exact while
+	                                      // fibm_full_dirty is false; lets the sweep skip the two force planes everywhere else
+	int64_t mask_pitch = 0;               // bytes per column = ceil(P / 64)
 	double *fxyf = nullptr;               // force_xy planes (2*S), only in FXY_FIELD mode
 	int32_t *cell_head = nullptr;         // ordered spread: head of the marker list of every cell (S ints)
 	double *u_in = nullptr, *rho_in = nullptr, *delU = nullptr;   // [Ny*2], [Ny], [Ny*2]

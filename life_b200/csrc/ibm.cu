@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(128) k_find_support(int64_t n, const double *_
 
 // ---- clearing force_ibm at the sites the last spread touched -------------------------------------------------------------------
 __global__ void k_zero_sites(int64_t n, const int32_t *__restrict__ scount, const int32_t *__restrict__ sidx,
-                             const int32_t *__restrict__ sjdx, Layout L, int64_t i_begin, double *fibm) {
+                             const int32_t *__restrict__ sjdx, Layout L, int64_t i_begin, double *fibm, uint8_t *mask, int64_t mask_pitch) {
 	const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (e >= n * SUPP) return;
 	const int64_t m = e / SUPP;
@@ -136,16 +136,18 @@ __global__ void k_zero_sites(int64_t n, const int32_t *__restrict__ scount, cons
 	const int64_t idx = L.node(il, sjdx[e]);
 	fibm[idx] = 0.0;
 	fibm[L.S + idx] = 0.0;
+	mask[(il + 1) * mask_pitch + (sjdx[e] >> 6)] = 0;     // every site of the span is being cleared by this launch
 }
 
 int ibm_clear_force(life_ctx *ctx) {
 	if (!ctx->fibm) return LIFE_OK;
 	if (ctx->fibm_full_dirty) {
 		LIFE_CUDA(ctx, cudaMemsetAsync(ctx->fibm, 0, sizeof(double) * 2 * ctx->L.S, ctx->stream));
+		LIFE_CUDA(ctx, cudaMemsetAsync(ctx->fibm_mask, 0, (size_t)(ctx->mask_pitch * (ctx->L.nxl + 2)), ctx->stream));
 	} else if (ctx->fibm_sites_dirty && ctx->mk.n > 0) {
 		const int64_t n = ctx->mk.n * SUPP;
 		k_zero_sites<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->mk.n, ctx->mk.scount, ctx->mk.sidx, ctx->mk.sjdx,
-		                                                                  ctx->L, ctx->i_begin, ctx->fibm);
+		                                                                  ctx->L, ctx->i_begin, ctx->fibm, ctx->fibm_mask, ctx->mask_pitch);
 		ctx->launches++;
 		LIFE_CUDA(ctx, cudaGetLastError());
 	}
@@ -333,6 +335,8 @@ struct SpreadArgs {
 	int64_t i_begin;
 	double Dx;
 	double *fibm;
+	uint8_t *mask;        // per (column, 64-row span) flag: force_ibm written there (ctx.h)
+	int64_t mask_pitch;
 	int32_t *head, *next, *err;
 };
 
@@ -349,6 +353,7 @@ __global__ void __launch_bounds__(128) k_spread_atomic(const SpreadArgs a) {
 	if (il < 0 || il >= a.L.nxl) return;
 	const int64_t idx = a.L.node(il, a.sjdx[m * SUPP + lane]);
 	const double d = a.sdirac[m * SUPP + lane];
+	a.mask[(il + 1) * a.mask_pitch + (a.sjdx[m * SUPP + lane] >> 6)] = 1;
 	atomicAdd(a.fibm + idx, spread_term(a.force[2 * m], a.eps[m], a.ds[m], d));
 	atomicAdd(a.fibm + a.L.S + idx, spread_term(a.force[2 * m + 1], a.eps[m], a.ds[m], d));
 }
@@ -421,6 +426,7 @@ __global__ void __launch_bounds__(128) k_spread_ordered(const SpreadArgs a) {
 	const int64_t idx = a.L.node(il, j);
 	a.fibm[idx] = sx;
 	a.fibm[a.L.S + idx] = sy;
+	a.mask[(il + 1) * a.mask_pitch + (j >> 6)] = 1;
 }
 
 int ibm_spread(life_ctx *ctx) {
@@ -437,6 +443,7 @@ int ibm_spread(life_ctx *ctx) {
 	a.i_begin = ctx->i_begin;
 	a.Dx = ctx->cfg.Dx;
 	a.fibm = ctx->fibm;
+	a.mask = ctx->fibm_mask; a.mask_pitch = ctx->mask_pitch;
 	a.next = m.next; a.err = m.err;
 	if (ctx->cfg.ordered) {
 		if (!ctx->cell_head) {

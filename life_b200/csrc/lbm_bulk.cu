@@ -37,6 +37,8 @@ struct BulkArgs {
 	double fup_x, fup_y;    // uniform force_xy entering u_n   (previous step's value)
 	double fuc_x, fuc_y;    // uniform force_xy of this step   (collision)
 	const double *fibm;     // IBM force planes or nullptr
+	const uint8_t *fmask;   // per (column, 64-row span) flag "force_ibm written here" (ctx.h), or nullptr: read the planes everywhere
+	int64_t mask_pitch;
 	// generic path only
 	const double *macro;    // stored rho_n, ux_n, uy_n planes (first step after an upload) or nullptr
 	double *fxyf;           // force_xy field planes or nullptr
@@ -50,15 +52,21 @@ struct BulkArgs {
 enum { M_NONE = 0, M_UNI = 1, M_IBM = 2, M_UNI_IBM = 3, M_GENERIC = 4 };
 
 // start-of-step macroscopics + collision of one node held in registers
+// does the 64-row span holding row j of column `col` carry any IBM force?  (warp-uniform in every kernel below: a warp's rows lie
+// in one span, or — QUAD — each thread's four rows do)
+__device__ __forceinline__ bool ibm_span(const BulkArgs &a, int64_t col, int64_t j) {
+	return a.fmask == nullptr || a.fmask[col * a.mask_pitch + (j >> 6)] != 0;
+}
+
 template <int COLL, int MODE>
-__device__ __forceinline__ void node_update(const BulkArgs &a, int64_t idx, const double (&f)[NV], double (&o)[NV]) {
+__device__ __forceinline__ void node_update(const BulkArgs &a, int64_t idx, const double (&f)[NV], double (&o)[NV], bool ibm_here = true) {
 	double sum, mx, my;
 	moments(f, sum, mx, my);
 	double Fux = 0.0, Fuy = 0.0, Fcx = 0.0, Fcy = 0.0;   // force entering u_n / force of the collision
 	double rho = sum, ux, uy;
 	if (MODE == M_GENERIC) {
 		double fix = 0.0, fiy = 0.0;
-		if (a.fibm) { fix = a.fibm[idx]; fiy = a.fibm[a.L.S + idx]; }
+		if (a.fibm && ibm_here) { fix = a.fibm[idx]; fiy = a.fibm[a.L.S + idx]; }
 		double fpx = a.fup_x, fpy = a.fup_y, fcx = a.fuc_x, fcy = a.fuc_y;
 		if (a.fxyf) { fpx = a.fxyf[idx]; fpy = a.fxyf[a.L.S + idx]; fcx = fpx; fcy = fpy; }
 		if (a.macro) {
@@ -83,7 +91,10 @@ __device__ __forceinline__ void node_update(const BulkArgs &a, int64_t idx, cons
 	} else {
 		if (MODE & M_UNI) { Fux = a.fup_x; Fuy = a.fup_y; Fcx = a.fuc_x; Fcy = a.fuc_y; }
 		if (MODE & M_IBM) {
-			const double fix = a.fibm[idx], fiy = a.fibm[a.L.S + idx];
+			// force_ibm is zero outside the <= 9 n support sites: the two planes are only read where the span's flag is set, so
+			// a lattice with bodies still moves ~144 B per node
+			double fix = 0.0, fiy = 0.0;
+			if (ibm_here) { fix = a.fibm[idx]; fiy = a.fibm[a.L.S + idx]; }
 			Fux += fix; Fuy += fiy; Fcx += fix; Fcy += fiy;
 		}
 #ifdef LIFE_EXACT
@@ -117,7 +128,7 @@ __global__ void __launch_bounds__(256) k_bulk_direct(const BulkArgs a) {
 	double f[NV], o[NV];
 #pragma unroll
 	for (int v = 0; v < NV; v++) f[v] = __ldg(a.fin + v * a.L.S + idx);
-	node_update<COLL, MODE>(a, idx, f, o);
+	node_update<COLL, MODE>(a, idx, f, o, ibm_span(a, col, j));
 #pragma unroll
 	for (int v = 0; v < NV; v++) a.fout[v * a.L.S + idx + LIFE_CX(v) * a.L.P + LIFE_CY(v)] = o[v];
 }
@@ -145,8 +156,10 @@ __device__ __forceinline__ void st_one(double *p, double x) {
 	else *p = x;
 }
 
-template <int COLL, int MODE, int BLOCK = 256, int HINT = 0>
-__global__ void __launch_bounds__(BLOCK) k_bulk_shuffle(const BulkArgs a) {
+// MINB = 0 leaves the register budget to the compiler (72 registers, 3 CTAs of 256 threads per SM); note that (256, 1) is NOT the
+// same thing: it lets ptxas spend 84 registers, which rounds to 2 CTAs per SM and costs 6 % (profiles/r02_bulk_tune_sweep_16384.txt)
+template <int COLL, int MODE, int BLOCK = 256, int HINT = 0, int MINB = 0>
+__global__ void __launch_bounds__(BLOCK, MINB) k_bulk_shuffle(const BulkArgs a) {
 	const int64_t col = a.c_first + blockIdx.x / a.tiles;
 	const int64_t j = ((int64_t)(blockIdx.x % a.tiles) * blockDim.x + threadIdx.x) * 2;
 	const int lane = threadIdx.x & 31;
@@ -162,8 +175,9 @@ __global__ void __launch_bounds__(BLOCK) k_bulk_shuffle(const BulkArgs a) {
 		const double2 t = ld_pair<HINT>(a.fin + v * a.L.S + idx);
 		f0[v] = t.x; f1[v] = t.y;
 	}
-	if (v0ok) node_update<COLL, MODE>(a, idx, f0, o0);
-	if (v1ok) node_update<COLL, MODE>(a, idx + 1, f1, o1);
+	const bool ih = ibm_span(a, col, j);
+	if (v0ok) node_update<COLL, MODE>(a, idx, f0, o0, ih);
+	if (v1ok) node_update<COLL, MODE>(a, idx + 1, f1, o1, ih);
 #pragma unroll
 	for (int v = 0; v < NV; v++) {
 		double *dst = a.fout + v * a.L.S + idx + LIFE_CX(v) * a.L.P;
@@ -184,6 +198,61 @@ __global__ void __launch_bounds__(BLOCK) k_bulk_shuffle(const BulkArgs a) {
 			if (lane == 31) { if (v1ok) st_one<HINT>(dst, o1[v]); }
 			else if (j + 2 < a.L.Ny) st_pair<HINT>(dst, o1[v], dn);
 			else if (v1ok) st_one<HINT>(dst, o1[v]);
+		}
+	}
+}
+
+
+// ---- QUAD: four nodes per thread, 32-byte accesses (sm_100: LDG.E.256 / STG.E.256) ------------------------------------------------
+// Same idea as SHUFFLE with twice the span: a warp owns 128 consecutive rows (R a multiple of 4) of one column, thread `lane`
+// holds rows R+4*lane .. R+4*lane+3: nine 32-byte loads, four collisions in registers, and per plane ONE aligned 32-byte store —
+// directly for cy = 0; for cy = +1 the aligned group {R+4l..R+4l+3} of the destination is {row 3 of lane l-1, rows 0, 1, 2 of
+// lane l} (one shuffle-up), for cy = -1 it is {rows 1, 2, 3 of lane l, row 0 of lane l+1} (one shuffle-down); only the two end
+// lanes of a warp store partial groups.  Needs Ny % 128 == 0 so that every lane of every warp owns four real rows (the launcher
+// falls back to SHUFFLE otherwise).  Selected with cfg.kernel = LIFE_KERNEL_QUAD; results identical to the other variants.
+__device__ __forceinline__ void ld_quad(const double *p, double (&x)[4]) {
+	asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x[0]), "=d"(x[1]), "=d"(x[2]), "=d"(x[3]) : "l"(p));
+}
+__device__ __forceinline__ void st_quad(double *p, double a, double b, double c, double d) {
+	asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
+template <int COLL, int MODE, int BLOCK = 128, int MINB = 3>
+__global__ void __launch_bounds__(BLOCK, MINB) k_bulk_quad(const BulkArgs a) {
+	const int64_t col = a.c_first + blockIdx.x / a.tiles;
+	const int64_t j = ((int64_t)(blockIdx.x % a.tiles) * BLOCK + threadIdx.x) * 4;
+	const int lane = threadIdx.x & 31;
+	if (j >= a.L.Ny) return;                      // whole warps (Ny % 128 == 0)
+	const int64_t idx = col * a.L.P + j + JOFF;   // multiple of 4 doubles -> 32-byte aligned
+	double f[4][NV], o[4][NV];
+#pragma unroll
+	for (int v = 0; v < NV; v++) {
+		double t[4];
+		ld_quad(a.fin + v * a.L.S + idx, t);
+#pragma unroll
+		for (int k = 0; k < 4; k++) f[k][v] = t[k];
+	}
+#pragma unroll
+	const bool ih = ibm_span(a, col, j);
+#pragma unroll
+	for (int k = 0; k < 4; k++) node_update<COLL, MODE>(a, idx + k, f[k], o[k], ih);
+#pragma unroll
+	for (int v = 0; v < NV; v++) {
+		double *dst = a.fout + v * a.L.S + idx + LIFE_CX(v) * a.L.P;
+		if (LIFE_CY(v) == 0) {
+			st_quad(dst, o[0][v], o[1][v], o[2][v], o[3][v]);
+		} else if (LIFE_CY(v) == 1) {
+			// destination rows j+1 .. j+4; aligned group (j .. j+3) = { row 3 of lane-1, own rows 0, 1, 2 }
+			const double up = __shfl_up_sync(0xffffffffu, o[3][v], 1);
+			if (lane == 0) { dst[1] = o[0][v]; *reinterpret_cast<double2 *>(dst + 2) = make_double2(o[1][v], o[2][v]); }
+			else st_quad(dst, up, o[0][v], o[1][v], o[2][v]);
+			if (lane == 31) dst[4] = o[3][v];
+		} else {
+			// destination rows j-1 .. j+2; aligned group (j .. j+3) = { own rows 1, 2, 3, row 0 of lane+1 }
+			const double dn = __shfl_down_sync(0xffffffffu, o[0][v], 1);
+			if (lane == 0) dst[-1] = o[0][v];
+			if (lane == 31) { *reinterpret_cast<double2 *>(dst) = make_double2(o[1][v], o[2][v]); dst[2] = o[3][v]; }
+			else st_quad(dst, o[1][v], o[2][v], o[3][v], dn);
 		}
 	}
 }
@@ -280,8 +349,9 @@ __global__ void __launch_bounds__(256, 2) k_bulk_tma(const BulkArgs a, const int
 		const int64_t jw = j - 2 * lane;
 		if (jw >= a.L.Ny) continue;                    // whole warp beyond the column (warp-uniform)
 		const int64_t idx = col * a.L.P + j + JOFF;
-		if (v0ok) node_update<COLL, MODE>(a, idx, f0, o0);
-		if (v1ok) node_update<COLL, MODE>(a, idx + 1, f1, o1);
+		const bool ih = ibm_span(a, col, j);
+		if (v0ok) node_update<COLL, MODE>(a, idx, f0, o0, ih);
+		if (v1ok) node_update<COLL, MODE>(a, idx + 1, f1, o1, ih);
 #pragma unroll
 		for (int v = 0; v < NV; v++) {
 			double *dst = a.fout + v * a.L.S + idx + LIFE_CX(v) * a.L.P;
@@ -332,14 +402,26 @@ static int launch_one(life_ctx *ctx, const BulkArgs &a0, int64_t c_count, cudaSt
 	if (ctx->cfg.kernel == LIFE_KERNEL_TMA) return launch_tma<COLL, MODE>(ctx, a0, c_count, st);
 #endif
 	BulkArgs a = a0;
+	if (ctx->cfg.kernel == LIFE_KERNEL_QUAD && a.L.Ny % 128 == 0) {
+		const int block = ctx->cfg.tune == 1 ? 128 : 256;
+		a.tiles = (a.L.Ny + 4 * block - 1) / (4 * block);
+		const int64_t blocks = a.tiles * c_count;
+		if (blocks <= 0) return LIFE_OK;
+		if (blocks > 0x7fffffffLL) return fail(ctx, LIFE_E_ARG, "bulk sweep: grid too large");
+		if (block == 256) k_bulk_quad<COLL, MODE, 256, 2><<<(unsigned)blocks, 256, 0, st>>>(a);
+		else k_bulk_quad<COLL, MODE, 128, 3><<<(unsigned)blocks, 128, 0, st>>>(a);
+		ctx->launches++;
+		LIFE_CUDA(ctx, cudaGetLastError());
+		return LIFE_OK;
+	}
 	const bool staged = ctx->cfg.kernel != LIFE_KERNEL_DIRECT;   // AUTO → SHUFFLE
 	// cfg.tune (measurement only, force-free shuffle kernel): tens digit = cache hint, units digit = CTA size 1:128 2:256 3:512
 #ifdef LIFE_EXACT
 	const int tune = 0;
 #else
-	const int tune = (staged && MODE == M_NONE) ? ctx->cfg.tune : 0;
+	const int tune = (staged && MODE == M_NONE && ctx->cfg.tune < 20) ? ctx->cfg.tune : 0;
 #endif
-	const int threads = (tune % 10 == 1) ? 128 : ((tune % 10 == 3) ? 512 : 256);
+	const int threads = (tune % 10 == 1) ? 128 : ((tune % 10 == 3) ? 512 : 256);      // 2, 4, 5: 256
 	const int64_t rows_per_block = staged ? 2 * threads : threads;
 	a.tiles = (a.L.Ny + rows_per_block - 1) / rows_per_block;
 	const int64_t blocks = a.tiles * c_count;
@@ -353,6 +435,9 @@ static int launch_one(life_ctx *ctx, const BulkArgs &a0, int64_t c_count, cudaSt
 	else if (tune == 11) k_bulk_shuffle<COLL, M_NONE, 128, 1><<<(unsigned)blocks, threads, 0, st>>>(a);
 	else if (tune == 12) k_bulk_shuffle<COLL, M_NONE, 256, 1><<<(unsigned)blocks, threads, 0, st>>>(a);
 	else if (tune == 13) k_bulk_shuffle<COLL, M_NONE, 512, 1><<<(unsigned)blocks, threads, 0, st>>>(a);
+	else if (tune == 4) k_bulk_shuffle<COLL, M_NONE, 256, 0, 4><<<(unsigned)blocks, threads, 0, st>>>(a);    // <= 64 registers: 4 CTAs / SM
+	else if (tune == 5) k_bulk_shuffle<COLL, M_NONE, 256, 0, 5><<<(unsigned)blocks, threads, 0, st>>>(a);
+	else if (tune == 14) k_bulk_shuffle<COLL, M_NONE, 256, 1, 4><<<(unsigned)blocks, threads, 0, st>>>(a);
 #endif
 	else return fail(ctx, LIFE_E_ARG, "bulk sweep: unknown cfg.tune");
 	ctx->launches++;
@@ -388,6 +473,9 @@ int launch_bulk(life_ctx *ctx,
 	a.fup_x = sc.fxy_prev[0]; a.fup_y = sc.fxy_prev[1];
 	a.fuc_x = sc.fxy_cur[0]; a.fuc_y = sc.fxy_cur[1];
 	a.fibm = ctx->fibm_any ? ctx->fibm : nullptr;
+	a.fmask = (a.fibm && !ctx->fibm_full_dirty) ? ctx->fibm_mask : nullptr;     // uploaded force_ibm: sites unknown, read everywhere
+	if (ctx->cfg.tune == 20) a.fmask = nullptr;     // measurement only: the round-1 behaviour (both force planes read at every node)
+	a.mask_pitch = ctx->mask_pitch;
 	a.c_first = c_first;
 	const bool generic = ctx->stored_macro_valid || ctx->fxy_mode == FXY_FIELD;
 	int mode;

@@ -31,6 +31,9 @@ int ensure_fibm(life_ctx *ctx) {
 	if (ctx->fibm) return LIFE_OK;
 	LIFE_CUDA(ctx, cudaMalloc(&ctx->fibm, sizeof(double) * 2 * ctx->L.S));
 	LIFE_CUDA(ctx, cudaMemsetAsync(ctx->fibm, 0, sizeof(double) * 2 * ctx->L.S, ctx->stream));
+	ctx->mask_pitch = (ctx->L.P + 63) / 64;
+	LIFE_CUDA(ctx, cudaMalloc(&ctx->fibm_mask, (size_t)(ctx->mask_pitch * (ctx->L.nxl + 2))));
+	LIFE_CUDA(ctx, cudaMemsetAsync(ctx->fibm_mask, 0, (size_t)(ctx->mask_pitch * (ctx->L.nxl + 2)), ctx->stream));
 	return LIFE_OK;
 }
 

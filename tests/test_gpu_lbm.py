@@ -60,8 +60,8 @@ def test_types_and_boundary_list_bit_exact(case):
     ctx.close()
 
 
-@pytest.mark.parametrize("kernel", [1, 2, 3], ids=["direct", "shuffle", "tma"])
-@pytest.mark.parametrize("shape", [(40, 36), (37, 41), (5, 7), (130, 515)])
+@pytest.mark.parametrize("kernel", [1, 2, 3, 4], ids=["direct", "shuffle", "tma", "quad"])
+@pytest.mark.parametrize("shape", [(40, 36), (37, 41), (5, 7), (130, 515), (9, 128), (33, 384)])
 def test_push_map_bit_exact(shape, kernel):
     """omega = 0 turns the BGK step into a pure push: tagged populations must land exactly where the reference's
     recv_id = ((i+cx+Nx)%Nx)*Ny + (j+cy+Ny)%Ny (src/Grid.cpp:240) sends them, wrap-around included."""
@@ -83,6 +83,39 @@ def test_push_map_bit_exact(shape, kernel):
         expect.reshape(-1, 9)[tgt.ravel(), v] = tags[:, :, v].ravel()
     assert np.array_equal(out, expect)
     ctx.close()
+
+
+@pytest.mark.parametrize("collision", [0, 1], ids=["bgk", "cm"])
+@pytest.mark.parametrize("setup", ["periodic+force", "cavity", "channel"])
+def test_kernel_variants_agree_bit_for_bit(setup, collision):
+    """DIRECT, SHUFFLE, TMA and QUAD (four nodes per thread, 32-byte accesses; needs Ny % 128 == 0, hence its own lattice here)
+    run the same per-node arithmetic: after 40 steps the populations must be identical, and equal to the oracle's within 1e-10."""
+    from life_b200 import capi
+    from oracle import oracle as O
+    from tests.initstate import wavy_state
+    Nx, Ny = 41, 256
+    walls = dict(wall_left=0, wall_right=0, wall_bottom=0, wall_top=0)
+    if setup == "cavity":
+        walls = dict(wall_top=O.VELOCITY)
+    elif setup == "channel":
+        walls = dict(wall_left=O.VELOCITY, wall_right=O.PRESSURE)
+    p = O.Params(Nx=Nx, Ny=Ny, omega=1.6, central_moments=collision, gravityX=3e-4 if setup == "periodic+force" else 0.0, nu_p=0.002, **walls)
+    o = O.Oracle(p)
+    f0, rho0, u0 = wavy_state(Nx, Ny, bool(collision), amp=0.02, non_equilibrium=0.01)
+    o.set("f", f0); o.set("rho", rho0); o.set("u", u0)
+    out = {}
+    for kernel in (1, 2, 3, 4):
+        ctx = capi.Context(K.life_config(p, o, kernel=kernel))
+        K.upload_from_oracle(ctx, o)
+        ctx.step_n(1, 40)
+        out[kernel] = ctx.download_state()
+        ctx.close()
+    o.step(40)
+    for kernel in (2, 3, 4):
+        for name in ("f", "rho", "u"):
+            assert np.array_equal(out[kernel][name], out[1][name]), (kernel, name)
+    for name in ("f", "rho", "u"):
+        assert K.rel_l2(out[4][name], o.get(name)) < K.TOL, name
 
 
 def test_restart_roundtrip_is_transparent():

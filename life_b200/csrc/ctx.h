@@ -58,7 +58,7 @@ struct MarkerBuffers {
 	double *force = nullptr, *irho = nullptr, *imom = nullptr;
 	int32_t *scount = nullptr, *sidx = nullptr, *sjdx = nullptr;
 	double *sdirac = nullptr;
-	int32_t *next = nullptr;          // cell-list links (ordered spread)
+	int32_t *next = nullptr;          // ordered spread: link of every (marker, site) entry in its site's list, [9 * cap]
 	int32_t *err = nullptr;           // device flag: support overflow
 	double *h_stage = nullptr;        // pinned host staging: 6*cap doubles up, 2*cap doubles down
 	int64_t h_cap = 0;
@@ -89,7 +89,7 @@ struct life_ctx {
 	                                      // fibm_full_dirty is false; lets the sweep skip the two force planes everywhere else
 	int64_t mask_pitch = 0;               // bytes per column = ceil(P / 64)
 	double *fxyf = nullptr;               // force_xy planes (2*S), only in FXY_FIELD mode
-	int32_t *cell_head = nullptr;         // ordered spread: head of the marker list of every cell (S ints)
+	int32_t *cell_head = nullptr;         // ordered spread: head of the entry list of every lattice site (S ints, -1 = empty)
 	double *u_in = nullptr, *rho_in = nullptr, *delU = nullptr;   // [Ny*2], [Ny], [Ny*2]
 	life::BcNode *bc = nullptr;
 	int64_t n_bc = 0;

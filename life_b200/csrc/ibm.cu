@@ -17,10 +17,10 @@
 //
 // Spread variants:
 //   atomic  (cfg.ordered == 0, the reference's `omp atomic` path): 2 atomicAdd(double) per support site.
-//   ordered (cfg.ordered == 1, the reference's `omp ordered` path): bit-repeatable, no floating-point atomics.  Markers are
-//           hashed into a cell list by their nearest lattice site; every (marker, site) entry walks the 3x3 cells around its
-//           site, the entry with the smallest marker index owns the site, sorts the contributors by marker index and writes
-//           their sum — the same value, in the same order, as the reference's marker-ordered loop.
+//   ordered (cfg.ordered == 1, the reference's `omp ordered` path): bit-repeatable, no floating-point atomics.  Every (marker,
+//           site) entry links itself into the list of its lattice site with one integer atomicExch; the entry left at the head
+//           owns the site, orders the site's few contributions by marker index and writes their sum — the same value, in the
+//           same order, as the reference's marker-ordered loop.
 #include "ctx.h"
 #include "d2q9.cuh"
 
@@ -54,7 +54,7 @@ static int ensure_markers(life_ctx *ctx, int64_t n) {
 	LIFE_CUDA(ctx, cudaMalloc(&m.sidx, sizeof(int32_t) * SUPP * cap));
 	LIFE_CUDA(ctx, cudaMalloc(&m.sjdx, sizeof(int32_t) * SUPP * cap));
 	LIFE_CUDA(ctx, cudaMalloc(&m.sdirac, sizeof(double) * SUPP * cap));
-	LIFE_CUDA(ctx, cudaMalloc(&m.next, sizeof(int32_t) * cap));
+	LIFE_CUDA(ctx, cudaMalloc(&m.next, sizeof(int32_t) * SUPP * cap));
 	LIFE_CUDA(ctx, cudaMemsetAsync(m.force, 0, sizeof(double) * 2 * cap, ctx->stream));
 	LIFE_CUDA(ctx, cudaMemsetAsync(m.scount, 0, sizeof(int32_t) * cap, ctx->stream));
 	LIFE_CUDA(ctx, cudaMallocHost(&m.h_stage, sizeof(double) * 8 * cap));   // 6*cap upload staging + 2*cap result staging
@@ -358,75 +358,57 @@ __global__ void __launch_bounds__(128) k_spread_atomic(const SpreadArgs a) {
 	atomicAdd(a.fibm + a.L.S + idx, spread_term(a.force[2 * m + 1], a.eps[m], a.ds[m], d));
 }
 
-// cell of a marker = its nearest lattice site, clamped into the ghost ring; -1 if it cannot touch this slab
-__device__ __forceinline__ int64_t marker_cell(const SpreadArgs &a, int64_t m) {
-	const int inear = (int)round(__ddiv_rn(a.pos[2 * m], a.Dx)), jnear = (int)round(__ddiv_rn(a.pos[2 * m + 1], a.Dx));
-	const int64_t c = (int64_t)inear - a.i_begin + 1, r = (int64_t)jnear + JOFF;
-	if (c < 0 || c > a.L.nxl + 1 || r < JOFF - 1 || r > JOFF + a.L.Ny) return -1;
-	return a.L.at(c, r);
-}
-
-__global__ void k_cells_build(const SpreadArgs a) {
-	const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (m >= a.n) return;
-	const int64_t cell = marker_cell(a, m);
-	a.next[m] = cell < 0 ? -1 : atomicExch(a.head + cell, (int32_t)m);
-}
-
-__global__ void k_cells_clear(const SpreadArgs a) {
-	const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (m >= a.n) return;
-	const int64_t cell = marker_cell(a, m);
-	if (cell >= 0) a.head[cell] = -1;
-}
-
-__global__ void __launch_bounds__(128) k_spread_ordered(const SpreadArgs a) {
+// Ordered spread, two launches.
+//   k_site_lists : every (marker, support site) entry e = m*9 + s pushes itself onto the list of its lattice site with one
+//                  atomicExch on the site's head (an int32 per node, -1 = empty): link[e] = previous head.
+//   k_spread_ordered : the entry that ended up as the head of its site's list owns the site: it walks the list (its length is the
+//                  number of markers touching the site, typically 3-6), orders the contributions by marker index — the order of the
+//                  reference's `omp ordered` loop (src/Objects.cpp:130-139; one contribution per marker and site) — adds them up from
+//                  0.0 exactly as the reference's `+=` does, writes force_ibm and the span mask, and resets the head to -1.
+// No floating-point atomics, no sort over all entries, no search: the only dependent chain is the list walk.
+__global__ void __launch_bounds__(256) k_site_lists(const SpreadArgs a) {
 	const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (e >= a.n * SUPP) return;
 	const int64_t m = e / SUPP;
-	const int s = (int)(e - m * SUPP);
-	if (s >= a.scount[m]) return;
-	const int i = a.sidx[e], j = a.sjdx[e];
-	const int64_t il = (int64_t)i - a.i_begin;
+	if ((int)(e - m * SUPP) >= a.scount[m]) return;
+	const int64_t il = (int64_t)a.sidx[e] - a.i_begin;
 	if (il < 0 || il >= a.L.nxl) return;
+	a.next[e] = atomicExch(a.head + a.L.node(il, a.sjdx[e]), (int32_t)e);
+}
+
+__global__ void __launch_bounds__(256) k_spread_ordered(const SpreadArgs a) {
+	const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= a.n * SUPP) return;
+	const int64_t m = e / SUPP;
+	if ((int)(e - m * SUPP) >= a.scount[m]) return;
+	const int j = a.sjdx[e];
+	const int64_t il = (int64_t)a.sidx[e] - a.i_begin;
+	if (il < 0 || il >= a.L.nxl) return;
+	const int64_t idx = a.L.node(il, j);
+	if (a.head[idx] != (int32_t)e) return;          // another entry owns this site
 	int32_t who[MAX_CONTRIB];
-	double wd[MAX_CONTRIB];
+	int32_t ent[MAX_CONTRIB];
 	int cnt = 0;
-	// every marker with (i,j) in its support has its nearest site within one cell of (i,j)
-	for (int di = -1; di <= 1; di++)
-		for (int dj = -1; dj <= 1; dj++) {
-			const int64_t cell = a.L.at(il + 1 + di, (int64_t)j + JOFF + dj);
-			for (int32_t m2 = a.head[cell]; m2 >= 0; m2 = a.next[m2]) {
-				const int c2 = a.scount[m2];
-				for (int s2 = 0; s2 < c2; s2++)
-					if (a.sidx[(int64_t)m2 * SUPP + s2] == i && a.sjdx[(int64_t)m2 * SUPP + s2] == j) {
-						if (m2 < m) return;   // a marker with a smaller index owns this site
-						if (cnt == MAX_CONTRIB) { atomicOr(a.err, 2); return; }
-						who[cnt] = m2;
-						wd[cnt] = a.sdirac[(int64_t)m2 * SUPP + s2];
-						cnt++;
-						break;
-					}
-			}
-		}
-	// ascending marker index = the order of the reference's `omp ordered` loop (src/Objects.cpp:130-139)
-	for (int x = 1; x < cnt; x++) {
-		const int32_t kw = who[x];
-		const double kd = wd[x];
-		int y = x - 1;
-		while (y >= 0 && who[y] > kw) { who[y + 1] = who[y]; wd[y + 1] = wd[y]; y--; }
-		who[y + 1] = kw; wd[y + 1] = kd;
+	for (int32_t x = (int32_t)e; x >= 0; x = a.next[x]) {
+		if (cnt == MAX_CONTRIB) { atomicOr(a.err, 2); break; }
+		// insertion by marker index (lists are short and arrive nearly sorted: entries were pushed in roughly ascending order)
+		const int32_t mk = x / SUPP;
+		int y = cnt - 1;
+		while (y >= 0 && who[y] > mk) { who[y + 1] = who[y]; ent[y + 1] = ent[y]; y--; }
+		who[y + 1] = mk; ent[y + 1] = x;
+		cnt++;
 	}
 	double sx = 0.0, sy = 0.0;
 	for (int x = 0; x < cnt; x++) {
 		const int64_t m2 = who[x];
-		sx = __dadd_rn(sx, spread_term(a.force[2 * m2], a.eps[m2], a.ds[m2], wd[x]));
-		sy = __dadd_rn(sy, spread_term(a.force[2 * m2 + 1], a.eps[m2], a.ds[m2], wd[x]));
+		const double d = a.sdirac[ent[x]];
+		sx = __dadd_rn(sx, spread_term(a.force[2 * m2], a.eps[m2], a.ds[m2], d));
+		sy = __dadd_rn(sy, spread_term(a.force[2 * m2 + 1], a.eps[m2], a.ds[m2], d));
 	}
-	const int64_t idx = a.L.node(il, j);
 	a.fibm[idx] = sx;
 	a.fibm[a.L.S + idx] = sy;
 	a.mask[(il + 1) * a.mask_pitch + (j >> 6)] = 1;
+	a.head[idx] = -1;                               // empty again for the next spread
 }
 
 int ibm_spread(life_ctx *ctx) {
@@ -451,11 +433,10 @@ int ibm_spread(life_ctx *ctx) {
 			LIFE_CUDA(ctx, cudaMemsetAsync(ctx->cell_head, 0xff, sizeof(int32_t) * ctx->L.S, ctx->stream));
 		}
 		a.head = ctx->cell_head;
-		const unsigned mb = (unsigned)((m.n + 127) / 128), eb = (unsigned)((m.n * SUPP + 127) / 128);
-		k_cells_build<<<mb, 128, 0, ctx->stream>>>(a);
-		k_spread_ordered<<<eb, 128, 0, ctx->stream>>>(a);
-		k_cells_clear<<<mb, 128, 0, ctx->stream>>>(a);
-		ctx->launches += 3;
+		const unsigned eb = (unsigned)((m.n * SUPP + 255) / 256);
+		k_site_lists<<<eb, 256, 0, ctx->stream>>>(a);
+		k_spread_ordered<<<eb, 256, 0, ctx->stream>>>(a);
+		ctx->launches += 2;
 	} else {
 		const int64_t threads = m.n * 32;
 		k_spread_atomic<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(a);

@@ -15,10 +15,9 @@
 //                                     =2 -> life_ibm_compute_epsilon (assembly and LU both on the GPU);
 //                                     =3 -> per body: GPU LU for small systems (<= 64 markers, many of them: Honami), GPU
 //                                     assembly + host LAPACK for large ones (UNI_EPSILON: TurekHron 132, PELskin 310)
-//   ObjectsClass::recomputeObjectVals / femKernel (src/Objects.cpp:152-232, :63-98), ONLY in the separate
-//                                     program LIFE_b200_fem (this file compiled with -DLIFE_B200_WITH_DEVICE_FEM) and there only with
-//                                     LIFE_B200_DEVICE_FEM=1 (off by default: the device solver has had its first B200 runs through
-//                                     the C ABI, tests/test_gpu_fem.py, but THIS binding has not run yet — DESIGN.md §10):
+//   ObjectsClass::recomputeObjectVals / femKernel (src/Objects.cpp:152-232, :63-98), selected with
+//                                     LIFE_B200_DEVICE_FEM=1 (off by default: the north star keeps the FEM host-side, and the device
+//                                     solver's own LU is within rounding of LAPACK, not bit-identical):
 //                                     predictor / relaxed update / dynamicFEM of all flexible bodies on the device
 //                                     (life_fem_predict / _relax / _dynamic), one CTA per filament; the host's FEM state and marker
 //                                     positions are refreshed from the device after each call, so every host writer and the
@@ -51,6 +50,7 @@
 #include "Utils.h"
 #include "FEMBody.h"
 #include "life_b200.h"
+#include "rank_team.h"
 #include <dlfcn.h>
 #include <chrono>
 #include <cstdio>
@@ -58,8 +58,13 @@
 
 namespace {
 
+RankTeam team;
+
 struct DeviceSide {
-	life_ctx *ctx = nullptr;
+	std::vector<life_ctx *> ctxs;        // one per rank = per GPU (LIFE_B200_GPUS, default 1); x-slabs of the lattice
+	std::vector<int64_t> i0, i1;         // columns [i0, i1) of each rank
+	life_ctx *ctx = nullptr;             // rank 0 (what single-context calls use)
+	int nranks = 1;
 	bool uploaded = false;       // the device holds a state (life_upload_state or life_read_restart has run)
 	bool macro_stale = false;    // host rho / u are older than the device state
 	bool full_stale = false;     // host f / force_ibm are older than the device state
@@ -73,6 +78,8 @@ struct DeviceSide {
 	double t_fem = 0;   // inside the optional device FEM bindings
 	long fem_calls = 0;
 } dev;
+// the same C-ABI call on every rank's context, concurrently
+#define ON_ALL_RANKS(r, ...) team.run([&](int r) { __VA_ARGS__; })
 
 double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 struct Timed {
@@ -82,7 +89,10 @@ struct Timed {
 };
 
 [[noreturn]] void die(const char *where, int rc) {
-	ERROR(std::string("liblife_b200: ") + where + " failed (" + std::to_string(rc) + "): " + life_last_error(dev.ctx));
+	team.abandon = true;      // the reference's ERROR() is exit(99): possibly from a rank's thread, with the other ranks mid-call
+	std::string msg;
+	for (life_ctx *c : dev.ctxs) { const char *m = c ? life_last_error(c) : ""; if (m && *m) { msg = m; break; } }
+	ERROR(std::string("liblife_b200: ") + where + " failed (" + std::to_string(rc) + "): " + msg);
 	std::abort();
 }
 #define LIFE_CK(call)                      \
@@ -132,7 +142,7 @@ life_config make_config(const GridClass &g) {
 #else
 	c.ordered = 0;
 #endif
-	c.device = -1;
+	c.device = -1;      // rank r of a multi-GPU run takes device r (ensure_context)
 	c.stream = nullptr;
 	c.rank = 0;
 	c.nranks = 1;
@@ -145,10 +155,11 @@ life_config make_config(const GridClass &g) {
 }
 
 void report() {
-	if (!dev.ctx) return;
-	life_sync(dev.ctx);
-	if (life_io_wait(dev.ctx) != LIFE_OK)   // the last asynchronous file write
-		std::fprintf(stderr, "\n[life_b200] file output failed: %s", life_last_error(dev.ctx));
+	if (!dev.ctx || team.abandon) return;
+	ON_ALL_RANKS(r, life_sync(dev.ctxs[r]));
+	bool io_failed = false;
+	ON_ALL_RANKS(r, if (life_io_wait(dev.ctxs[r]) != LIFE_OK) io_failed = true);   // the last asynchronous file write (collective)
+	if (io_failed) std::fprintf(stderr, "\n[life_b200] file output failed: %s", life_last_error(dev.ctx));
 	const double wall = now() - dev.t_begin;
 	std::fprintf(stderr, "\n[life_b200] wall %.3f s since the device context was created, of which context + first upload / restart read %.3f s; "
 	                     "inside life_step %.3f s, interp %.3f s, spread %.3f s, epsilon %.3f s, output calls %.3f s (writeInfo %.3f, writeVTK %.3f, "
@@ -160,9 +171,10 @@ void report() {
 		             1e6 * (wall - dev.t_first) / (double)dev.steps, (double)Nx * Ny * dev.steps / (wall - dev.t_first) / 1e6,
 		             (long)Nx, (long)Ny, dev.steps);
 	if (dev.fem_calls) std::fprintf(stderr, "\n[life_b200] device FEM: %ld life_fem_dynamic calls, %.3f s inside the FEM bindings", dev.fem_calls, dev.t_fem);
-	std::fprintf(stderr, "\n[life_b200] %ld life_step, %ld life_ibm_interp, %ld life_ibm_spread, %ld life_ibm_compute_epsilon, %lld kernel launches\n",
-	             dev.steps, dev.interps, dev.spreads, dev.eps_solves, (long long)life_launch_count(dev.ctx));
-	life_destroy(dev.ctx);
+	std::fprintf(stderr, "\n[life_b200] %ld life_step, %ld life_ibm_interp, %ld life_ibm_spread, %ld life_ibm_compute_epsilon, %lld kernel launches (rank 0), %d GPU(s)\n",
+	             dev.steps, dev.interps, dev.spreads, dev.eps_solves, (long long)life_launch_count(dev.ctx), dev.nranks);
+	ON_ALL_RANKS(r, life_destroy(dev.ctxs[r]));
+	dev.ctxs.clear();
 	dev.ctx = nullptr;
 }
 
@@ -186,11 +198,27 @@ bool host_io() {
 void ensure_context(const GridClass &g) {
 	if (dev.ctx) return;
 	const double t0 = now();
-	const life_config c = make_config(g);
-	int rc = life_create(&c, &dev.ctx);
-	if (rc != LIFE_OK) {
-		ERROR(std::string("liblife_b200: life_create failed (") + std::to_string(rc) + "): " + life_last_error(nullptr));
-	}
+	const life_config c0 = make_config(g);
+	// LIFE_B200_GPUS=N: the lattice is cut into N x-slabs, one per GPU of this box, one host thread each
+	const char *ng = std::getenv("LIFE_B200_GPUS");
+	dev.nranks = ng ? std::max(1, std::atoi(ng)) : 1;
+	unsigned char nccl_id[128] = {0};
+	if (dev.nranks > 1 && life_nccl_unique_id(nccl_id) != LIFE_OK)
+		ERROR(std::string("liblife_b200: life_nccl_unique_id failed: ") + life_last_error(nullptr));
+	dev.ctxs.assign((size_t)dev.nranks, nullptr);
+	dev.i0.assign((size_t)dev.nranks, 0);
+	dev.i1.assign((size_t)dev.nranks, 0);
+	team.start(dev.nranks);
+	std::vector<std::string> errs((size_t)dev.nranks);
+	ON_ALL_RANKS(r, {
+		life_config c = c0;
+		if (dev.nranks > 1) { c.rank = r; c.nranks = dev.nranks; c.device = r; c.nccl_id = nccl_id; }
+		if (life_create(&c, &dev.ctxs[(size_t)r]) != LIFE_OK) errs[(size_t)r] = life_last_error(nullptr);     // (thread-local message)
+		else life_slab(dev.ctxs[(size_t)r], &dev.i0[(size_t)r], &dev.i1[(size_t)r]);
+	});
+	for (int r = 0; r < dev.nranks; r++)
+		if (!dev.ctxs[(size_t)r]) ERROR(std::string("liblife_b200: life_create failed on rank ") + std::to_string(r) + ": " + errs[(size_t)r]);
+	dev.ctx = dev.ctxs[0];
 	dev.t_begin = t0;      // the wall clock of report() starts before the CUDA context is created
 	std::atexit(report);
 }
@@ -201,7 +229,12 @@ void ensure_state(GridClass &g) {
 	if (dev.uploaded) return;
 	const double t0 = now();
 	ensure_context(g);
-	LIFE_CK(life_upload_state(dev.ctx, g.f.data(), g.rho.data(), g.u.data(), g.force_xy.data(), g.force_ibm.data(), g.u_in.data(), g.rho_in.data()));
+	// x is the slow index (src/Grid.cpp:70): a rank's slab is one contiguous chunk of every reference array
+	ON_ALL_RANKS(r, {
+		const size_t o = (size_t)dev.i0[(size_t)r] * Ny;
+		LIFE_CK(life_upload_state(dev.ctxs[(size_t)r], g.f.data() + o * nVels, g.rho.data() + o, g.u.data() + o * dims, g.force_xy.data() + o * dims,
+		                          g.force_ibm.data() + o * dims, g.u_in.data(), g.rho_in.data()));
+	});
 	dev.uploaded = true;
 	dev.t_first += now() - t0;
 }
@@ -212,7 +245,7 @@ void ensure_state(GridClass &g) {
 void GridClass::lbmKernel() {
 	ensure_state(*this);   // first step of a run whose output goes through the host mirrors, or of a restart read on the host
 	Timed timed(dev.t_step);
-	LIFE_CK(life_step(dev.ctx, t));
+	ON_ALL_RANKS(r, LIFE_CK(life_step(dev.ctxs[(size_t)r], t)));
 	dev.steps++;
 	dev.macro_stale = dev.full_stale = true;
 }
@@ -229,7 +262,8 @@ void send_markers(std::vector<IBMNodeClass> &iNode) {
 		dev.ds[i] = iNode[i].ds;
 		dev.eps[i] = iNode[i].epsilon;
 	}
-	LIFE_CK(life_ibm_set_markers(dev.ctx, (int64_t)n, dev.pos.data(), dev.vel.data(), dev.ds.data(), dev.eps.data()));
+	// every rank holds all markers and gathers / spreads on the support sites it owns
+	ON_ALL_RANKS(r, LIFE_CK(life_ibm_set_markers(dev.ctxs[(size_t)r], (int64_t)n, dev.pos.data(), dev.vel.data(), dev.ds.data(), dev.eps.data())));
 }
 }  // namespace
 
@@ -271,7 +305,8 @@ void ObjectsClass::computeEpsilon() {
 		first.push_back((int64_t)mem.size());
 	}
 	if (dfirst.size() > 1) {
-		LIFE_CK(life_ibm_compute_epsilon(dev.ctx, (int64_t)dfirst.size() - 1, dfirst.data(), dmem.data(), dev.eps.data()));
+		// (the matrix only depends on the markers: every rank solves the same systems and updates its own copy of epsilon)
+		ON_ALL_RANKS(r, LIFE_CK(life_ibm_compute_epsilon(dev.ctxs[(size_t)r], (int64_t)dfirst.size() - 1, dfirst.data(), dmem.data(), r == 0 ? dev.eps.data() : nullptr)));
 		for (size_t k = 0; k < dmem.size(); k++) iNode[(size_t)dmem[k]].epsilon = dev.eps[(size_t)dmem[k]];
 	}
 	if (hfirst.size() > 1) {
@@ -293,7 +328,6 @@ void ObjectsClass::computeEpsilon() {
 	dev.eps_solves++;
 }
 
-#ifdef LIFE_B200_WITH_DEVICE_FEM   // compiled only into LIFE_b200_fem (life_b200/host/Makefile): the default program is untouched by it
 // ---- ObjectsClass::recomputeObjectVals / femKernel (optional, LIFE_B200_DEVICE_FEM=1) ------------------------------------------------
 namespace {
 
@@ -354,12 +388,12 @@ void fem_setup(ObjectsClass &o) {
 		desc.push_back(d);
 	}
 	send_markers(o.iNode);     // the marker arrays the solver reads and writes must exist on the device
-	LIFE_CK(life_fem_create(dev.ctx, (int32_t)desc.size(), desc.data()));
+	ON_ALL_RANKS(r, LIFE_CK(life_fem_create(dev.ctxs[(size_t)r], (int32_t)desc.size(), desc.data())));      // every rank holds every body, like the markers
 	for (size_t k = 0; k < dfem.body.size(); k++) {
 		FEMBodyClass *s = dfem.body[k]->sBody;
 		dfem.state.resize(11 * (size_t)s->bodyDOFs);
 		for (int v = 0; v < 11; v++) std::copy(fem_vector(s, v)->begin(), fem_vector(s, v)->end(), dfem.state.begin() + (size_t)v * s->bodyDOFs);
-		LIFE_CK(life_fem_set_state(dev.ctx, (int32_t)k, dfem.state.data()));
+		ON_ALL_RANKS(r, LIFE_CK(life_fem_set_state(dev.ctxs[(size_t)r], (int32_t)k, dfem.state.data())));
 	}
 	dfem.ready = true;
 }
@@ -401,11 +435,11 @@ void ObjectsClass::recomputeObjectVals() {
 		Timed timed(dev.t_fem);
 		fem_setup(*this);
 		if (subIt == 0) {
-			LIFE_CK(life_fem_predict(dev.ctx, gPtr->t));                       // resetValues + predictor, src/Objects.cpp:160-174
+			ON_ALL_RANKS(r, LIFE_CK(life_fem_predict(dev.ctxs[(size_t)r], gPtr->t)));                    // resetValues + predictor, src/Objects.cpp:160-174
 		} else {
 			if (subIt == 1) relax = static_cast<double>(Utils::sgn(relax) * min(fabs(relax), relaxMax));   // src/Objects.cpp:183-188
 			else relax = -relax * subNum / subDen;
-			LIFE_CK(life_fem_relax(dev.ctx, relax));                           // src/Objects.cpp:195-208
+			ON_ALL_RANKS(r, LIFE_CK(life_fem_relax(dev.ctxs[(size_t)r], relax)));                    // src/Objects.cpp:195-208
 		}
 		fem_refresh_host(*this, true);
 	}
@@ -432,7 +466,7 @@ void ObjectsClass::femKernel() {
 	// marker forces and epsilon are on the device already (the life_ibm_interp that precedes this call, src/Objects.cpp:40-47)
 	double sums[3];
 	dfem.per_body.resize(5 * dfem.body.size());
-	LIFE_CK(life_fem_dynamic(dev.ctx, sums, dfem.per_body.data()));
+	ON_ALL_RANKS(r, { double other[3]; LIFE_CK(life_fem_dynamic(dev.ctxs[(size_t)r], r == 0 ? sums : other, r == 0 ? dfem.per_body.data() : nullptr)); });
 	for (size_t k = 0; k < dfem.body.size(); k++) {
 		FEMBodyClass *s = dfem.body[k]->sBody;
 		s->subRes = dfem.per_body[5 * k]; s->subNum = dfem.per_body[5 * k + 1]; s->subDen = dfem.per_body[5 * k + 2];
@@ -444,14 +478,14 @@ void ObjectsClass::femKernel() {
 	subDen = sums[2];
 	dev.fem_calls++;
 }
-#endif  // LIFE_B200_WITH_DEVICE_FEM
 
 // ---- ObjectsClass::ibmKernelInterp ----------------------------------------------------------------------------------------------
 void ObjectsClass::ibmKernelInterp() {
 	Timed timed(dev.t_interp);
 	const size_t n = iNode.size();
 	send_markers(iNode);
-	LIFE_CK(life_ibm_interp(dev.ctx, dev.force.data()));
+	// collective: partial sums of markers whose support straddles a slab face are added across ranks; every rank ends with all forces
+	ON_ALL_RANKS(r, LIFE_CK(life_ibm_interp(dev.ctxs[(size_t)r], r == 0 ? dev.force.data() : nullptr)));
 	for (size_t i = 0; i < n; i++) {
 		iNode[i].force[eX] = dev.force[2 * i];      // consumed by the host FEM (src/FEMElement.cpp:53) and writeTotalForces
 		iNode[i].force[eY] = dev.force[2 * i + 1];
@@ -465,7 +499,7 @@ void ObjectsClass::ibmKernelSpread() {
 	// supports, ds, epsilon: those of the last ibmKernelInterp (the host recomputes them only in recomputeObjectVals, which
 	// always precedes an interp); forces: those the last interp left on the device
 	Timed timed(dev.t_spread);
-	LIFE_CK(life_ibm_spread(dev.ctx));
+	ON_ALL_RANKS(r, LIFE_CK(life_ibm_spread(dev.ctxs[(size_t)r])));
 	dev.spreads++;
 	dev.macro_stale = dev.full_stale = true;
 }
@@ -476,7 +510,7 @@ void GridClass::writeInfo() {
 	Timed timed(dev.t_io), part(dev.t_info);
 	if (host_io()) {
 		if (dev.uploaded && dev.macro_stale) {
-			LIFE_CK(life_download_macro(dev.ctx, rho.data(), u.data()));
+			ON_ALL_RANKS(r, LIFE_CK(life_download_macro(dev.ctxs[(size_t)r], rho.data() + (size_t)dev.i0[(size_t)r] * Ny, u.data() + (size_t)dev.i0[(size_t)r] * Ny * dims)));
 			dev.macro_stale = false;
 		}
 		using Fn = void (*)(GridClass *);
@@ -488,11 +522,15 @@ void GridClass::writeInfo() {
 	double vmax = 0.0;
 	int32_t blown = 0;
 	int64_t bi = -1, bj = -1;
-	LIFE_CK(life_max_speed(dev.ctx, &vmax, &blown, &bi, &bj));
+	ON_ALL_RANKS(r, {      // collective: every rank gets the global answer
+		double v; int32_t b; int64_t x, y;
+		LIFE_CK(life_max_speed(dev.ctxs[(size_t)r], &v, &b, &x, &y));
+		if (r == 0) { vmax = v; blown = b; bi = x; bj = y; }
+	});
 	if (blown) {
 #ifdef VTK
 		Utils::writeVTK(*this);
-		life_io_wait(dev.ctx);
+		ON_ALL_RANKS(r, life_io_wait(dev.ctxs[(size_t)r]));
 #endif
 		ERROR("Simulation blew up (t = " + to_string(t) + ") at i = " + to_string(bi) + ", j = " + to_string(bj) + "...exiting");
 	}
@@ -514,7 +552,7 @@ void GridClass::writeVTK() {
 	Timed timed(dev.t_io), part(dev.t_vtk);
 	if (host_io() || bigEndian) {
 		if (dev.uploaded && dev.macro_stale) {
-			LIFE_CK(life_download_macro(dev.ctx, rho.data(), u.data()));
+			ON_ALL_RANKS(r, LIFE_CK(life_download_macro(dev.ctxs[(size_t)r], rho.data() + (size_t)dev.i0[(size_t)r] * Ny, u.data() + (size_t)dev.i0[(size_t)r] * Ny * dims)));
 			dev.macro_stale = false;
 		}
 		using Fn = void (*)(GridClass *);
@@ -523,7 +561,8 @@ void GridClass::writeVTK() {
 		return;
 	}
 	const string name = "Results/VTK/Fluid." + to_string(t) + ".vti";
-	LIFE_CK(life_write_vtk(dev.ctx, name.c_str(), rho_p, ref_P, LIFE_IO_ASYNC));
+	// every rank writes its own byte ranges of the one file (csrc/lbm_file.cu)
+	ON_ALL_RANKS(r, LIFE_CK(life_write_vtk(dev.ctxs[(size_t)r], name.c_str(), rho_p, ref_P, LIFE_IO_ASYNC)));
 	// placeholders for body files of an earlier run, as src/Grid.cpp:900-912
 	if (!oPtr->hasIBM && boost::filesystem::exists("Results/VTK/IBM.0.vtp")) {
 		string blank = "Results/VTK/IBM." + to_string(t) + ".vtp";
@@ -542,7 +581,10 @@ void GridClass::writeRestart() {
 	Timed timed(dev.t_io), part(dev.t_restart);
 	if (host_io() || bigEndian) {
 		if (dev.uploaded && dev.full_stale) {
-			LIFE_CK(life_download_state(dev.ctx, f.data(), rho.data(), u.data(), force_ibm.data()));
+			ON_ALL_RANKS(r, {
+				const size_t o = (size_t)dev.i0[(size_t)r] * Ny;
+				LIFE_CK(life_download_state(dev.ctxs[(size_t)r], f.data() + o * nVels, rho.data() + o, u.data() + o * dims, force_ibm.data() + o * dims));
+			});
 			dev.full_stale = dev.macro_stale = false;
 		}
 		using Fn = void (*)(GridClass *);
@@ -550,7 +592,7 @@ void GridClass::writeRestart() {
 		orig(this);
 		return;
 	}
-	LIFE_CK(life_write_restart(dev.ctx, "Results/Restart/Fluid.restart", t, LIFE_IO_ASYNC));
+	ON_ALL_RANKS(r, LIFE_CK(life_write_restart(dev.ctxs[(size_t)r], "Results/Restart/Fluid.restart", t, LIFE_IO_ASYNC)));
 }
 
 void GridClass::readRestart() {
@@ -566,8 +608,13 @@ void GridClass::readRestart() {
 	Timed timed(dev.t_first);
 	ensure_context(*this);
 	int32_t t_file = 0;
-	const int rc = life_read_restart(dev.ctx, "Results/Restart/Fluid.restart", force_xy.data(), u_in.data(), rho_in.data(), &t_file);
-	if (rc != LIFE_OK) ERROR(life_last_error(dev.ctx));   // the reference's own messages (src/Grid.cpp:1080, :1104, :1138)
+	int rc = LIFE_OK;
+	ON_ALL_RANKS(r, {      // every rank reads its own slab of the file
+		int32_t tf = 0;
+		const int rr = life_read_restart(dev.ctxs[(size_t)r], "Results/Restart/Fluid.restart", force_xy.data(), u_in.data(), rho_in.data(), &tf);
+		if (r == 0) { rc = rr; t_file = tf; } else if (rr != LIFE_OK) rc = rc == LIFE_OK ? rr : rc;
+	});
+	if (rc != LIFE_OK) die("life_read_restart", rc);   // the reference's own messages (src/Grid.cpp:1080, :1104, :1138)
 	tOffset = t_file;
 	t = tOffset;
 	dev.uploaded = true;

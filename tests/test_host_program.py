@@ -101,9 +101,7 @@ def test_program_reproduces_reference_results(case, device_eps, tmp_path):
     times = 2 if case == "TurekHron" else 1          # second run restarts from Results/Restart (store-ref-data.sh:51-53)
     ref = _run(case, "LIFE_ref", str(tmp_path / "ref"), times)
     assert ref.returncode == 0, ref.stdout[-2000:]
-    exe = "LIFE_b200_fem" if device_fem else "LIFE_b200"      # the FEM bindings live in a separate executable (life_b200/host/Makefile)
-    if not _have(case, exe):
-        pytest.skip("life_b200/host/_build/%s/%s not built" % (case, exe))
+    exe = "LIFE_b200"
     new = _run(case, exe, str(tmp_path / "b200"), times, LIFE_B200_DEVICE_EPSILON=str(device_eps),
                LIFE_B200_HOST_IO="1" if host_io else "0", LIFE_B200_DEVICE_FEM="1" if device_fem else "0")
     assert new.returncode == 0, new.stdout[-2000:] + new.stderr[-2000:]
@@ -194,6 +192,48 @@ def test_program_in_exact_mode_is_bitwise_the_reference(case, variant, tmp_path)
     # the numbers writeInfo prints (max velocity from life_max_speed) are the same text
     for pat in (r"Max Velocity = (\S+)", r"Max Velocity \(m/s\) = (\S+)", r"Max Reynolds number = (\S+)"):
         assert re.findall(pat, new.stdout) == re.findall(pat, ref.stdout), pat
+
+
+def _ngpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gpus", [2, 4])
+@pytest.mark.parametrize("case", ["ChannelFlow", "Cylinder", "PELskin", "Honami"])
+def test_program_on_several_gpus(case, gpus, tmp_path):
+    """LIFE's own main() and host code around N slabs on N GPUs (LIFE_B200_GPUS=N: one host thread per rank inside life_host.cpp,
+    NCCL halo exchange, every rank writing its byte ranges of the shared fluid files) — multi-GPU without Python.
+    Body-free case, exact mode: bit for bit the reference program (per-node arithmetic does not depend on the decomposition).
+    Bodies: a marker whose support straddles a slab face is gathered as two partial sums added by NCCL, so forces agree to
+    rounding, not bitwise: rigid body within 1e-10 after 500 steps, flexible bodies on the early trajectory (see above)."""
+    if _ngpus() < gpus:
+        pytest.skip("needs %d GPUs" % gpus)
+    if not (_have(case, "LIFE_b200") and _have(case, "LIFE_ref")):
+        pytest.skip("life_b200/host/_build/%s not built" % case)
+    ref = _run(case, "LIFE_ref", str(tmp_path / "ref"))
+    assert ref.returncode == 0, ref.stdout[-2000:]
+    new = _run(case, "LIFE_b200", str(tmp_path / "b200"), LIFE_B200_GPUS=str(gpus), LIFE_B200_EXACT="1")
+    assert new.returncode == 0, new.stdout[-2000:] + new.stderr[-2000:]
+    assert "%d GPU(s)" % gpus in new.stderr
+    differing, n_files = _diff_r(str(tmp_path / "ref"), str(tmp_path / "b200"))
+    t_end, err = _compare(case, str(tmp_path / "ref"), str(tmp_path / "b200"))
+    print("\n%s on %d GPUs, exact mode: %d files, differing %s; %s" % (case, gpus, n_files, differing, err))
+    assert t_end == 500
+    if case == "ChannelFlow":
+        assert not differing, differing
+    elif case == "Cylinder":
+        bad = {k: v for k, v in err.items() if not v <= (1e-8 if k == "TotalForces.out" else K.TOL)}
+        assert not bad, bad
+    else:
+        ta = R.read_table(str(tmp_path / "ref" / "Results" / "TotalForces.out"))
+        tb = R.read_table(str(tmp_path / "b200" / "Results" / "TotalForces.out"))
+        early = (ta[:, 0] > 0) & (ta[:, 0] <= 20)
+        assert np.abs(tb[early, 1:] - ta[early, 1:]).max() <= 1e-7 * np.abs(ta[:, 1:]).max()
 
 
 def test_program_refuses_to_run_without_a_gpu(tmp_path):

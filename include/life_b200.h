@@ -331,6 +331,30 @@ int life_fem_dynamic(life_ctx *ctx, double *sums, double *per_body);
 /* Marker positions / velocities as the device holds them (after life_fem_*), [2 * n] each; either may be NULL. */
 int life_ibm_get_markers(life_ctx *ctx, double *pos, double *vel);
 
+/*
+ * The sub-iteration loop of ObjectsClass::objectKernel (src/Objects.cpp:33-52) with the markers RESIDENT on the device: per
+ * sub-iteration nothing crosses PCIe but the three residual sums (and, for large UNI_EPSILON systems whose LU stays on the host,
+ * the epsilon matrix).
+ *   life_fsi_move   recomputeObjectVals (src/Objects.cpp:152-232) without its last line: predictor at time step t (sub_it == 0) or
+ *                   the Aitken-relaxed update with `relax` (sub_it >= 1) of every flexible body, then IBMNodeClass::findSupport
+ *                   (src/IBMNode.cpp:139-179) of every marker and computeDs (:182-204, bit-exact) of the flexible bodies' markers,
+ *                   all from the positions the device holds.  Asynchronous.
+ *   (epsilon)       computeEpsilon is the caller's choice: life_ibm_compute_epsilon(..., NULL) keeps it on the device;
+ *                   life_ibm_assemble_epsilon + the host's LAPACK + life_ibm_set_epsilon keeps the solve bit-identical to the reference.
+ *   life_fsi_force  ibmKernelInterp (src/Objects.cpp:102-117; forces stay on the device) + femKernel (:63-98; = life_fem_dynamic):
+ *                   sums [3] = subRes, subNum, subDen over the bodies in body order, per_body [5 * n_bodies] (may be NULL).  Synchronises.
+ * life_ibm_spread closes the step as before.  life_ibm_get_markers / life_ibm_get_marker_state / life_fem_get_state bring the body
+ * state back when a host writer needs it (TotalForces.out, IBM / FEM restart files, body VTK).
+ */
+int life_fsi_move(life_ctx *ctx, int32_t t, int32_t sub_it, double relax);
+int life_fsi_force(life_ctx *ctx, double *sums, double *per_body);
+
+/* Overwrite the epsilon of all n markers on the device (the host solved the systems life_ibm_assemble_epsilon returned). */
+int life_ibm_set_epsilon(life_ctx *ctx, const double *epsilon);
+
+/* Marker forces [2 * n] (lattice units), ds [n], epsilon [n] as the device holds them; any pointer may be NULL. */
+int life_ibm_get_marker_state(life_ctx *ctx, double *force, double *ds, double *epsilon);
+
 /* ---- test hooks (bit-exact integer-map checks)------------------------------------------------------------------------ */
 
 /* Supports as IBMNodeClass::supp holds them: count [n]; idx, jdx, dirac [n*9] in the reference's i-outer/j-inner order. */

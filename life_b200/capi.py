@@ -31,7 +31,7 @@ EXPORTS = [
     "life_vtk_frame", "life_write_vtk", "life_write_restart", "life_io_wait", "life_io_busy", "life_io_stats", "life_io_set_staging",
     "life_read_restart",
     "life_fem_create", "life_fem_set_state", "life_fem_get_state", "life_fem_predict", "life_fem_relax", "life_fem_dynamic",
-    "life_ibm_get_markers",
+    "life_ibm_get_markers", "life_fsi_move", "life_fsi_force", "life_ibm_set_epsilon", "life_ibm_get_marker_state",
 ]
 
 
@@ -143,6 +143,10 @@ def load():
     L.life_fem_relax.argtypes = [vp, dbl]
     L.life_fem_dynamic.argtypes = [vp, vp, vp]
     L.life_ibm_get_markers.argtypes = [vp, vp, vp]
+    L.life_fsi_move.argtypes = [vp, i32, i32, dbl]
+    L.life_fsi_force.argtypes = [vp, vp, vp]
+    L.life_ibm_set_epsilon.argtypes = [vp, vp]
+    L.life_ibm_get_marker_state.argtypes = [vp, vp, vp, vp]
     _lib = L
     return L
 
@@ -417,6 +421,25 @@ class Context:
         sums, per = np.zeros(3), np.zeros((len(self._fem_dofs), 5))
         self._ck(self.L.life_fem_dynamic(self.h, _ptr(sums), _ptr(per)))
         return sums, per
+
+    def fsi_move(self, t, sub_it, relax=0.0):
+        self._ck(self.L.life_fsi_move(self.h, int(t), int(sub_it), C.c_double(relax)))
+
+    def fsi_force(self):
+        """interp + dynamicFEM on the device -> (sums, per-body array) like fem_dynamic"""
+        sums, per = np.zeros(3), np.zeros((len(self._fem_dofs), 5))
+        self._ck(self.L.life_fsi_force(self.h, _ptr(sums), _ptr(per)))
+        return sums, per
+
+    def ibm_set_epsilon(self, eps):
+        eps = _f64(eps)
+        assert eps.size == self.n_markers
+        self._ck(self.L.life_ibm_set_epsilon(self.h, _ptr(eps)))
+
+    def ibm_get_marker_state(self):
+        force, ds, eps = np.zeros((self.n_markers, 2)), np.zeros(self.n_markers), np.zeros(self.n_markers)
+        self._ck(self.L.life_ibm_get_marker_state(self.h, _ptr(force), _ptr(ds), _ptr(eps)))
+        return force, ds, eps
 
     def ibm_get_markers(self):
         pos, vel = np.zeros((self.n_markers, 2)), np.zeros((self.n_markers, 2))

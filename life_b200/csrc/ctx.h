@@ -173,7 +173,8 @@ int ensure_macro(life_ctx *ctx);
 int ensure_fibm(life_ctx *ctx);
 // ibm.cu
 int ibm_set_markers(life_ctx *ctx, int64_t n, const double *pos, const double *vel, const double *ds, const double *eps);
-int ibm_interp(life_ctx *ctx, double *force_out);
+int ibm_interp(life_ctx *ctx, double *force_out, bool no_sync = false);
+int ibm_refresh_supports(life_ctx *ctx);
 int ibm_spread(life_ctx *ctx);
 int ibm_clear_force(life_ctx *ctx);
 int ibm_check(life_ctx *ctx);

@@ -56,6 +56,15 @@ __global__ void __launch_bounds__(64) k_fem(const Body *__restrict__ bodies, con
 	}
 }
 
+// IBMNodeClass::computeDs (src/IBMNode.cpp:182-204) of the markers of every flexible body, after the solver moved them
+__global__ void __launch_bounds__(64) k_fem_ds(const Body *__restrict__ bodies, const int *__restrict__ mfirst, const int *__restrict__ mids,
+                                               const double *__restrict__ pos, double Dx, double *ds) {
+	__shared__ Body b;
+	if (threadIdx.x == 0) b = bodies[blockIdx.x];
+	__syncthreads();
+	life_fem::compute_ds(b, Lane{(int)threadIdx.x, (int)blockDim.x}, pos, Dx, ds, mids + mfirst[blockIdx.x]);
+}
+
 void fem_free(life_ctx *ctx) {
 	FemState *f = ctx->fem;
 	if (!f) return;
@@ -240,6 +249,57 @@ int life_fem_dynamic(life_ctx *ctx, double *sums, double *per_body) {
 		sums[0] = sums[1] = sums[2] = 0.0;
 		for (int k = 0; k < f->n_bodies; k++) { sums[0] += r[5 * (size_t)k]; sums[1] += r[5 * (size_t)k + 1]; sums[2] += r[5 * (size_t)k + 2]; }
 	}
+	return LIFE_OK;
+}
+
+// ---- the sub-iteration loop without the markers leaving the device (src/Objects.cpp:33-52) ------------------------------------------
+int life_fsi_move(life_ctx *ctx, int32_t t, int32_t sub_it, double relax) {
+	if (!ctx) return LIFE_E_ARG;
+	int rc = fem_ready(ctx, "life_fsi_move");
+	if (rc) return rc;
+	LIFE_CUDA(ctx, cudaSetDevice(ctx->device));
+	// recomputeObjectVals, src/Objects.cpp:152-232: predictor (first sub-iteration) or the relaxed update, then findSupport and
+	// computeDs of the moved markers.  computeEpsilon is the caller's next call (device LU or device assembly + host LAPACK).
+	if (sub_it == 0) rc = fem_launch<FEM_PREDICT>(ctx, t, 0.0);
+	else rc = fem_launch<FEM_RELAX>(ctx, 0, relax);
+	if (rc) return rc;
+	if ((rc = ibm_refresh_supports(ctx))) return rc;
+	FemState *f = ctx->fem;
+	k_fem_ds<<<(unsigned)f->n_bodies, 64, 0, ctx->stream>>>(f->d_bodies, f->d_marker_first, f->d_marker_ids, ctx->mk.pos, ctx->cfg.Dx, ctx->mk.ds);
+	ctx->launches++;
+	LIFE_CUDA(ctx, cudaGetLastError());
+	return LIFE_OK;
+}
+
+int life_fsi_force(life_ctx *ctx, double *sums, double *per_body) {
+	if (!ctx) return LIFE_E_ARG;
+	if (!ctx->have_state) return fail(ctx, LIFE_E_STATE, "life_fsi_force: no state uploaded");
+	int rc = fem_ready(ctx, "life_fsi_force");
+	if (rc) return rc;
+	LIFE_CUDA(ctx, cudaSetDevice(ctx->device));
+	if ((rc = ibm_interp(ctx, nullptr, true))) return rc;        // ibmKernelInterp, forces stay on the device
+	if ((rc = life_fem_dynamic(ctx, sums, per_body))) return rc;  // femKernel; its read-back of the residual sums is the one synchronisation
+	return ibm_check(ctx);
+}
+
+int life_ibm_set_epsilon(life_ctx *ctx, const double *epsilon) {
+	if (!ctx || !epsilon) return LIFE_E_ARG;
+	if (ctx->mk.n == 0) return LIFE_OK;
+	LIFE_CUDA(ctx, cudaSetDevice(ctx->device));
+	LIFE_CUDA(ctx, cudaMemcpyAsync(ctx->mk.eps, epsilon, sizeof(double) * ctx->mk.n, cudaMemcpyHostToDevice, ctx->stream));
+	LIFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return LIFE_OK;
+}
+
+int life_ibm_get_marker_state(life_ctx *ctx, double *force, double *ds, double *epsilon) {
+	if (!ctx) return LIFE_E_ARG;
+	if (ctx->mk.n == 0) return LIFE_OK;
+	LIFE_CUDA(ctx, cudaSetDevice(ctx->device));
+	const int64_t n = ctx->mk.n;
+	if (force) LIFE_CUDA(ctx, cudaMemcpyAsync(force, ctx->mk.force, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, ctx->stream));
+	if (ds) LIFE_CUDA(ctx, cudaMemcpyAsync(ds, ctx->mk.ds, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+	if (epsilon) LIFE_CUDA(ctx, cudaMemcpyAsync(epsilon, ctx->mk.eps, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+	LIFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	return LIFE_OK;
 }
 

@@ -156,7 +156,8 @@ int ibm_clear_force(life_ctx *ctx) {
 	return LIFE_OK;
 }
 
-int ibm_set_markers(life_ctx *ctx, int64_t n, const double *pos, const double *vel, const double *ds, const double *eps) {
+// the markers are about to move: what happens to the force_ibm spread with the old supports
+static int ibm_before_move(life_ctx *ctx) {
 	int rc;
 	// force_ibm is non-zero at the OLD supports: clear it before they are replaced — unless no step has used it yet (markers
 	// set between a spread, an upload or life_read_restart and the next life_step: the reference keeps force_ibm until
@@ -166,6 +167,31 @@ int ibm_set_markers(life_ctx *ctx, int64_t n, const double *pos, const double *v
 	} else if (ctx->fibm_sites_dirty) {
 		ctx->fibm_full_dirty = true;
 	}
+	return LIFE_OK;
+}
+
+static int launch_find_support(life_ctx *ctx) {
+	MarkerBuffers &m = ctx->mk;
+	const int64_t threads = m.n * 32;
+	k_find_support<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(m.n, m.pos, ctx->cfg.Dx, ctx->cfg.Nx, ctx->cfg.Ny,
+	                                                                           m.scount, m.sidx, m.sjdx, m.sdirac, m.err);
+	ctx->launches++;
+	LIFE_CUDA(ctx, cudaGetLastError());
+	return LIFE_OK;
+}
+
+// supports of the positions the DEVICE holds (the structural solver moved the markers there, fem.cu): findSupport of every marker
+// without the positions crossing PCIe
+int ibm_refresh_supports(life_ctx *ctx) {
+	int rc;
+	if (ctx->mk.n == 0) return LIFE_OK;
+	if ((rc = ibm_before_move(ctx))) return rc;
+	return launch_find_support(ctx);
+}
+
+int ibm_set_markers(life_ctx *ctx, int64_t n, const double *pos, const double *vel, const double *ds, const double *eps) {
+	int rc;
+	if ((rc = ibm_before_move(ctx))) return rc;
 	if ((rc = ensure_markers(ctx, n))) return rc;
 	MarkerBuffers &m = ctx->mk;
 	m.n = n;
@@ -181,13 +207,8 @@ int ibm_set_markers(life_ctx *ctx, int64_t n, const double *pos, const double *v
 	LIFE_CUDA(ctx, cudaMemcpyAsync(m.in, h, sizeof(double) * 6 * n, cudaMemcpyHostToDevice, ctx->stream));
 	LIFE_CUDA(ctx, cudaEventRecord(m.ev_stage, ctx->stream));
 	m.stage_busy = true;
-	const int64_t threads = n * 32;
-	k_find_support<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(n, m.pos, ctx->cfg.Dx, ctx->cfg.Nx, ctx->cfg.Ny,
-	                                                                           m.scount, m.sidx, m.sjdx, m.sdirac, m.err);
-	ctx->launches++;
-	LIFE_CUDA(ctx, cudaGetLastError());
 	// asynchronous: a support overflow (src/IBMNode.cpp:171-172) is reported by the next synchronising marker call
-	return LIFE_OK;
+	return launch_find_support(ctx);
 }
 
 // reads back the device error flag (after a synchronisation of ctx->stream has been enqueued by the caller)
@@ -280,7 +301,8 @@ __global__ void k_force_calc(int64_t n, const double *irho, const double *imom, 
 	force[2 * m + 1] = __dmul_rn(2.0, __dsub_rn(__dmul_rn(sc, vel[2 * m + 1]), imom[2 * m + 1]));
 }
 
-int ibm_interp(life_ctx *ctx, double *force_out) {
+// `no_sync`: leave everything enqueued (the structural solver consumes the forces on the device; errors surface at its own sync)
+int ibm_interp(life_ctx *ctx, double *force_out, bool no_sync) {
 	int rc;
 	if ((rc = ibm_clear_force(ctx))) return rc;     // fill(force_ibm, 0), src/Objects.cpp:105
 	MarkerBuffers &m = ctx->mk;
@@ -311,6 +333,7 @@ int ibm_interp(life_ctx *ctx, double *force_out) {
 		ctx->launches++;
 		LIFE_CUDA(ctx, cudaGetLastError());
 	}
+	if (no_sync) return LIFE_OK;
 	int32_t *herr = reinterpret_cast<int32_t *>(ctx->h_pin);
 	LIFE_CUDA(ctx, cudaMemcpyAsync(herr, m.err, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
 	if (force_out) {

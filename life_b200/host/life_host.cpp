@@ -77,6 +77,8 @@ struct DeviceSide {
 	double t_info = 0, t_vtk = 0, t_restart = 0;   // parts of t_io
 	double t_fem = 0;   // inside the optional device FEM bindings
 	long fem_calls = 0;
+	double t_object = 0;   // inside ObjectsClass::objectKernel (whichever implementation runs it)
+	long sub_its = 0;
 } dev;
 // the same C-ABI call on every rank's context, concurrently
 #define ON_ALL_RANKS(r, ...) team.run([&](int r) { __VA_ARGS__; })
@@ -171,6 +173,8 @@ void report() {
 		             1e6 * (wall - dev.t_first) / (double)dev.steps, (double)Nx * Ny * dev.steps / (wall - dev.t_first) / 1e6,
 		             (long)Nx, (long)Ny, dev.steps);
 	if (dev.fem_calls) std::fprintf(stderr, "\n[life_b200] device FEM: %ld life_fem_dynamic calls, %.3f s inside the FEM bindings", dev.fem_calls, dev.t_fem);
+	if (dev.sub_its) std::fprintf(stderr, "\n[life_b200] objectKernel: %.3f s, %ld sub-iterations = %.1f us per sub-iteration (interp / FEM / support / epsilon / spread, host and device)",
+	                              dev.t_object, dev.sub_its, 1e6 * dev.t_object / (double)dev.sub_its);
 	std::fprintf(stderr, "\n[life_b200] %ld life_step, %ld life_ibm_interp, %ld life_ibm_spread, %ld life_ibm_compute_epsilon, %lld kernel launches (rank 0), %d GPU(s)\n",
 	             dev.steps, dev.interps, dev.spreads, dev.eps_solves, (long long)life_launch_count(dev.ctx), dev.nranks);
 	ON_ALL_RANKS(r, life_destroy(dev.ctxs[r]));
@@ -331,13 +335,19 @@ void ObjectsClass::computeEpsilon() {
 // ---- ObjectsClass::recomputeObjectVals / femKernel (optional, LIFE_B200_DEVICE_FEM=1) ------------------------------------------------
 namespace {
 
-bool device_fem() {
-	static const bool on = [] { const char *e = std::getenv("LIFE_B200_DEVICE_FEM"); return e && std::atoi(e) != 0; }();
-	return on;
+// LIFE_B200_DEVICE_FEM: 0 (default) the reference's host FEM; 1 the structural solver on the device, host state refreshed after every
+// call (the reference's own support / ds / epsilon code keeps running on the host); 2 the whole sub-iteration loop RESIDENT on the
+// device (ObjectsClass::objectKernel below): per sub-iteration only the residual sums come back, the host's body state is refreshed
+// when a writer needs it
+int device_fem_level() {
+	static const int lvl = [] { const char *e = std::getenv("LIFE_B200_DEVICE_FEM"); return e ? std::atoi(e) : 0; }();
+	return lvl;
 }
+bool device_fem() { return device_fem_level() != 0; }
 
 struct DeviceFem {
 	bool ready = false;
+	bool host_stale = false;               // resident loop: the host's markers / FEM state are older than the device's
 	std::vector<IBMBodyClass *> body;      // the flexible bodies, in iBody order (= the order femKernel adds their residuals)
 	std::vector<double> state, pos, vel, per_body;
 } dfem;
@@ -424,6 +434,102 @@ void fem_refresh_host(ObjectsClass &o, bool geometry_from_U_km1) {
 
 }  // namespace
 
+namespace {
+// device -> host, everything the reference's writers read of the bodies (TotalForces.out: marker force, epsilon, ds; IBM.restart / body
+// VTK: pos, vel, force; FEM.restart / tips: the state vectors and the geometry that follows from U)
+void fem_refresh_all(ObjectsClass &o) {
+	if (!dfem.host_stale) return;
+	fem_refresh_host(o, false);
+	const size_t n = o.iNode.size();
+	std::vector<double> force(2 * n), ds(n), eps(n);
+	LIFE_CK(life_ibm_get_marker_state(dev.ctx, force.data(), ds.data(), eps.data()));
+	for (size_t i = 0; i < n; i++) {
+		o.iNode[i].force[eX] = force[2 * i]; o.iNode[i].force[eY] = force[2 * i + 1];
+		o.iNode[i].ds = ds[i];
+		o.iNode[i].epsilon = eps[i];
+	}
+	dfem.host_stale = false;
+}
+}  // namespace
+
+// ---- ObjectsClass::objectKernel (optional, LIFE_B200_DEVICE_FEM=2): the sub-iteration loop resident on the device ----------------------
+void ObjectsClass::objectKernel() {
+	Timed whole(dev.t_object);
+	struct Count { int &it; ~Count() { dev.sub_its += it > 0 ? it : 1; } } count{subIt};
+	if (device_fem_level() < 2 || !dev.uploaded || !hasFlex) {
+		using Fn = void (*)(ObjectsClass *);
+		static Fn orig = next_symbol<Fn>("_ZN12ObjectsClass12objectKernelEv");
+		orig(this);
+		return;
+	}
+	Timed timed(dev.t_fem);
+	fem_setup(*this);
+	// epsilon groups exactly as computeEpsilon forms them after t = 0 (src/Objects.cpp:238-262)
+	if (dev.grp_first.size() < 2) {
+		dev.grp_first.assign(1, 0);
+		dev.grp_members.clear();
+#ifdef UNI_EPSILON
+		for (size_t i = 0; i < iNode.size(); i++) dev.grp_members.push_back((int64_t)i);
+		dev.grp_first.push_back((int64_t)dev.grp_members.size());
+#else
+		for (size_t ib = 0; ib < iBody.size(); ib++) {
+			if (iBody[ib].flex != eFlexible) continue;
+			for (size_t k = 0; k < iBody[ib].node.size(); k++) dev.grp_members.push_back((int64_t)(iBody[ib].node[k] - &iNode[0]));
+			dev.grp_first.push_back((int64_t)dev.grp_members.size());
+		}
+#endif
+	}
+	const int64_t nb = (int64_t)dev.grp_first.size() - 1;
+	int64_t largest = 0;
+	for (int64_t b = 0; b < nb; b++) largest = std::max(largest, dev.grp_first[b + 1] - dev.grp_first[b]);
+	static const int lu_limit = [] { const char *e = std::getenv("LIFE_B200_DEVICE_LU_MAX"); return e ? std::atoi(e) : 96; }();
+	subIt = 0;
+	const int MAXIT = 20;
+	double sums[3] = {0, 0, 0};
+	dfem.per_body.resize(5 * dfem.body.size());
+	do {
+		// the Aitken factor, src/Objects.cpp:178-188
+		if (subIt == 1) relax = static_cast<double>(Utils::sgn(relax) * min(fabs(relax), relaxMax));
+		else if (subIt > 1) relax = -relax * subNum / subDen;
+		ON_ALL_RANKS(r, LIFE_CK(life_fsi_move(dev.ctxs[(size_t)r], gPtr->t, subIt, relax)));
+		if (largest <= lu_limit) {
+			ON_ALL_RANKS(r, LIFE_CK(life_ibm_compute_epsilon(dev.ctxs[(size_t)r], nb, dev.grp_first.data(), dev.grp_members.data(), nullptr)));
+		} else {
+			// large UNI_EPSILON systems: matrix from the device, the reference's own LAPACK solve on the host (src/Objects.cpp:303-311)
+			std::vector<size_t> off((size_t)nb + 1, 0);
+			for (int64_t b = 0; b < nb; b++) { const size_t d = (size_t)(dev.grp_first[b + 1] - dev.grp_first[b]); off[(size_t)b + 1] = off[(size_t)b] + d * d; }
+			dev.eps_mat.resize(off[(size_t)nb]);
+			dev.eps.resize(iNode.size());
+			LIFE_CK(life_ibm_get_marker_state(dev.ctx, nullptr, nullptr, dev.eps.data()));
+			LIFE_CK(life_ibm_assemble_epsilon(dev.ctx, nb, dev.grp_first.data(), dev.grp_members.data(), dev.eps_mat.data()));
+			for (int64_t b = 0; b < nb; b++) {
+				const size_t d = (size_t)(dev.grp_first[b + 1] - dev.grp_first[b]);
+				std::vector<double> A(dev.eps_mat.begin() + off[(size_t)b], dev.eps_mat.begin() + off[(size_t)b + 1]), rhs(d, 1.0);
+				const std::vector<double> sol = Utils::solveLAPACK(A, rhs);
+				for (size_t i = 0; i < d; i++) dev.eps[(size_t)dev.grp_members[(size_t)dev.grp_first[b] + i]] = sol[i];
+			}
+			ON_ALL_RANKS(r, LIFE_CK(life_ibm_set_epsilon(dev.ctxs[(size_t)r], dev.eps.data())));
+		}
+		dev.eps_solves++;
+		ON_ALL_RANKS(r, { double other[3]; LIFE_CK(life_fsi_force(dev.ctxs[(size_t)r], r == 0 ? sums : other, r == 0 ? dfem.per_body.data() : nullptr)); });
+		dev.interps++;
+		dev.fem_calls++;
+		subRes = sqrt(sums[0]) / (ref_L * sqrt(static_cast<double>(simDOFs)));      // src/Objects.cpp:95-97
+		subNum = sums[1];
+		subDen = sums[2];
+		subIt++;
+	} while (subIt < MAXIT && subRes > subTol);
+	for (size_t k = 0; k < dfem.body.size(); k++) {
+		FEMBodyClass *s = dfem.body[k]->sBody;
+		s->resNR = dfem.per_body[5 * k + 3]; s->itNR = (int)dfem.per_body[5 * k + 4];
+	}
+	ON_ALL_RANKS(r, LIFE_CK(life_ibm_spread(dev.ctxs[(size_t)r])));
+	dev.spreads++;
+	dev.macro_stale = dev.full_stale = true;
+	dfem.host_stale = true;
+	if (subIt == MAXIT) ERROR("Subiteration scheme hit " + to_string(subIt) + " iterations...exiting");
+}
+
 void ObjectsClass::recomputeObjectVals() {
 	if (!device_fem() || !dev.uploaded) {
 		using Fn = void (*)(ObjectsClass *);
@@ -506,6 +612,8 @@ void ObjectsClass::ibmKernelSpread() {
 
 // ---- output and restart: device-fed by default, through the host mirrors with LIFE_B200_HOST_IO=1 -------------------------------------
 void GridClass::writeInfo() {
+	if (oPtr && oPtr->hasFlex) fem_refresh_all(*oPtr);      // the resident sub-iteration loop leaves the host's body state behind
+
 	if (!host_io()) ensure_state(*this);
 	Timed timed(dev.t_io), part(dev.t_info);
 	if (host_io()) {
@@ -548,6 +656,8 @@ void GridClass::writeInfo() {
 }
 
 void GridClass::writeVTK() {
+	if (oPtr && oPtr->hasFlex) fem_refresh_all(*oPtr);      // the resident sub-iteration loop leaves the host's body state behind
+
 	if (!(host_io() || bigEndian)) ensure_state(*this);
 	Timed timed(dev.t_io), part(dev.t_vtk);
 	if (host_io() || bigEndian) {
@@ -577,6 +687,8 @@ void GridClass::writeVTK() {
 }
 
 void GridClass::writeRestart() {
+	if (oPtr && oPtr->hasFlex) fem_refresh_all(*oPtr);      // the resident sub-iteration loop leaves the host's body state behind
+
 	if (!(host_io() || bigEndian)) ensure_state(*this);
 	Timed timed(dev.t_io), part(dev.t_restart);
 	if (host_io() || bigEndian) {

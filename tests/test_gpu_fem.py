@@ -128,3 +128,95 @@ def test_device_structural_solver_matches_the_reference(case, steps):
                        timeout=900, env=dict(os.environ, OPENBLAS_NUM_THREADS="1"))
     print(p.stdout[-1500:])
     assert p.returncode == 0 and p.stdout.strip().endswith("OK"), p.stdout[-3000:] + p.stderr[-3000:]
+
+
+RESIDENT = r'''
+import sys
+sys.path.insert(0, %(root)r)
+import numpy as np
+from oracle.refharness import RefCase
+from life_b200 import capi
+from tests import cases as K
+case, steps = %(case)r, %(steps)d
+r = RefCase(case)
+g = K.golden(case)
+o = K.make_oracle(g)
+ctx = capi.Context(K.life_config(o.params, o, device=0))
+nb = r.fem_count()
+desc = [r.fem_body(fb) for fb in range(nb)]
+m = r.markers()
+n = len(m["ds"])
+ctx.ibm_set_markers(m["pos"], m["vel"], m["ds"], m["epsilon"])
+ctx.ibm_set_forces(m["force"])
+ctx.fem_create(desc)
+uni = bool(r.flags & RefCase.FLAG_UNI_EPS)
+groups = [np.arange(n)] if uni else [np.asarray(d["marker"]) for d in desc]
+worst = {}
+def close(a, b, what, floor, tol):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    err = float(np.abs(a - b).max() / max(np.abs(b).max(), floor))
+    worst[what] = max(worst.get(what, 0.0), err)
+    assert err < tol, (what, err)
+subits = 0
+for step in range(steps):
+    r.t = r.t + 1
+    r.lbm_kernel()
+    # the GPU lattice takes the reference's mid-step state (post-stream populations, IBM force not yet spread)
+    ctx.upload_state(r.f(), None, None, r.force_xy(), None, r.u_in(), r.rho_in())
+    r.subit = 0
+    while True:
+        # both sides start the sub-iteration from the reference's state
+        for fb in range(nb):
+            ctx.fem_set_state(fb, r.fem_get_state(fb, desc[fb]["n_dof"]))
+        m0 = r.markers()
+        ctx.ibm_set_markers(m0["pos"], m0["vel"], m0["ds"], m0["epsilon"])
+        ctx.ibm_set_forces(m0["force"])
+        r.recompute_object_vals()                      # predictor / relax + findSupport + computeDs + computeEpsilon on the host
+        ctx.fsi_move(r.t, r.subit, r.relax)            # the same on the device, from the device's own marker arrays
+        ctx.ibm_compute_epsilon(groups)
+        m1 = r.markers()
+        pos, vel = ctx.ibm_get_markers()
+        force, ds, eps = ctx.ibm_get_marker_state()
+        L = desc[0]["ref_L"]
+        close(pos, m1["pos"], "marker pos after move", L, 1e-11)
+        close(ds, m1["ds"], "ds", 1.0, 1e-9)
+        close(eps, m1["epsilon"], "epsilon (device LU vs LAPACK)", 1.0, 1e-7)
+        cnt, idx, jdx, dirac = ctx.ibm_get_supports()
+        rc, ri, rj, rd = r.supports()
+        same = np.array_equal(cnt, rc) and np.array_equal(idx, ri) and np.array_equal(jdx, rj)
+        worst["markers with a different support set"] = worst.get("markers with a different support set", 0) + (0 if same else int((cnt != rc).sum() + (idx != ri).any(axis=1).sum()))
+        if same:
+            close(dirac, rd, "delta weights", 1.0, 1e-9)
+        r.ibm_interp()
+        sums, per = ctx.fsi_force()                    # interp + dynamicFEM, forces never leave the device
+        f_dev = ctx.ibm_get_marker_state()[0]
+        close(f_dev, r.markers()["force"], "marker force (interp)", 1e-6, 1e-7)
+        r.fem_kernel()
+        ref_sub = r.subres
+        sub = np.sqrt(sums[0]) / (L * np.sqrt(float(desc[0]["sim_dofs"])))
+        close([sub], [ref_sub], "subRes", 1e-9, 1e-5)
+        pos2, _ = ctx.ibm_get_markers()
+        close(pos2, r.markers()["pos"], "marker pos after dynamicFEM", L, 1e-10)
+        subits += 1
+        r.subit = r.subit + 1
+        if not (r.subit < 20 and r.subres > r.subTol):
+            break
+    r.ibm_spread()
+assert worst.get("markers with a different support set", 0) == 0, worst
+print("%%s: %%d steps, %%d sub-iterations resident on the device; worst relative differences: %%s" %% (case, steps, subits, {k: float("%%.1e" %% v) for k, v in worst.items()}))
+ctx.close(); r.close()
+print("OK")
+'''
+
+
+@pytest.mark.parametrize("case,steps", [("InvertedFlag", 8), ("Honami", 3), ("TurekHron", 10), ("PELskin", 4)])
+def test_resident_subiteration_loop_matches_the_reference(case, steps):
+    """life_fsi_move / life_ibm_compute_epsilon / life_fsi_force — the sub-iteration loop with the markers resident on the device — inside
+    live FSI runs of the compiled reference: after every device call the marker positions, ds, epsilon, supports, forces and the
+    residual agree with what the reference's host code (recomputeObjectVals, ibmKernelInterp, femKernel) produced from the same state."""
+    if not refharness.available(case):
+        pytest.skip("oracle/_ref/libref_%s.so not built" % case)
+    p = subprocess.run([sys.executable, "-c", RESIDENT % dict(root=ROOT, case=case, steps=steps)], capture_output=True, text=True,
+                       timeout=900, env=dict(os.environ, OPENBLAS_NUM_THREADS="1"))
+    print(p.stdout[-1500:])
+    assert p.returncode == 0 and p.stdout.strip().endswith("OK"), p.stdout[-3000:] + p.stderr[-3000:]

@@ -78,8 +78,8 @@ def _compare(case, ref_dir, new_dir):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("device_eps", [0, 1, 2, 3, "host-io", "device-fem"],
-                         ids=["host-eps", "device-assembly+lapack", "device-eps", "auto-eps", "host-io", "device-fem"])
+@pytest.mark.parametrize("device_eps", [0, 1, 2, 3, "host-io", "device-fem", "device-fem-resident"],
+                         ids=["host-eps", "device-assembly+lapack", "device-eps", "auto-eps", "host-io", "device-fem", "device-fem-resident"])
 @pytest.mark.parametrize("case", EXAMPLES)
 def test_program_reproduces_reference_results(case, device_eps, tmp_path):
     """Default build of the drop-in: device-fed files (life_write_vtk / life_write_restart / life_read_restart / life_max_speed);
@@ -91,7 +91,8 @@ def test_program_reproduces_reference_results(case, device_eps, tmp_path):
         device_eps = 0
         if case not in ("ChannelFlow", "TurekHron"):
             pytest.skip("the host-mirror I/O variant is exercised on one plain and one restarted body case")
-    device_fem = device_eps == "device-fem"
+    resident = device_eps == "device-fem-resident"     # LIFE_B200_DEVICE_FEM=2: the whole sub-iteration loop on the device
+    device_fem = device_eps in ("device-fem", "device-fem-resident")
     if device_fem:
         device_eps = 1
         if case not in FLEXIBLE:
@@ -103,11 +104,13 @@ def test_program_reproduces_reference_results(case, device_eps, tmp_path):
     assert ref.returncode == 0, ref.stdout[-2000:]
     exe = "LIFE_b200"
     new = _run(case, exe, str(tmp_path / "b200"), times, LIFE_B200_DEVICE_EPSILON=str(device_eps),
-               LIFE_B200_HOST_IO="1" if host_io else "0", LIFE_B200_DEVICE_FEM="1" if device_fem else "0")
+               LIFE_B200_HOST_IO="1" if host_io else "0", LIFE_B200_DEVICE_FEM=("2" if resident else "1") if device_fem else "0")
     assert new.returncode == 0, new.stdout[-2000:] + new.stderr[-2000:]
     assert ("life_fem_dynamic calls" in new.stderr) == device_fem
     assert "life_step" in new.stderr and " 0 life_step" not in new.stderr      # the CUDA path really ran
     assert (" 0 life_ibm_compute_epsilon" in new.stderr) == (not device_eps)
+    if resident:
+        assert " 0 life_ibm_interp" not in new.stderr and "us per sub-iteration" in new.stderr
     print("\n%s wall time of the last run (500 steps incl. all host work and I/O): LIFE_ref %.2f s (%d host threads), LIFE_b200 %.2f s   %s"
           % (case, ref.seconds, os.cpu_count(), new.seconds, new.stderr.strip().splitlines()[-1]))
     t_end, err = _compare(case, str(tmp_path / "ref"), str(tmp_path / "b200"))

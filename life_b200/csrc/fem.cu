@@ -1,10 +1,11 @@
 // The structural solver of the flexible bodies on the device: one CTA per filament running fem_core.h.
 //
-// STATUS: compiled into the library, its logic and barrier placement are checked on the CPU (tests/test_fem_core.py: the same
-// source run serially and as real threads under ThreadSanitizer against the compiled reference) and two short first runs on a
-// B200 agree with the reference to rounding (profiles/r01_fem_first_device_runs.txt: InvertedFlag; Honami, 128 filaments); the
-// full device tests are tests/test_gpu_fem.py.  Nothing in the default paths calls it yet: the host program keeps the reference's
-// own FEM (life_host.cpp does not bind femKernel).
+// STATUS: its logic and barrier placement are checked on the CPU (tests/test_fem_core.py: the same source run serially and as real
+// threads under ThreadSanitizer against the compiled reference), the device entry points inside live runs of the compiled reference
+// on a B200 (tests/test_gpu_fem.py, all four flexible examples), and the host program binds it on request (life_host.cpp,
+// LIFE_B200_DEVICE_FEM = 1: solver on the device; = 2: the whole sub-iteration loop resident on the device, life_fsi_move /
+// life_fsi_force below).  The default keeps the reference's host FEM: the north star leaves it host-side, and for ONE filament the
+// host is faster (profiles/r02_fsi_timing_programs.txt); with many filaments (Honami, 128) the resident loop is 3x faster.
 //
 // Data: every body's constant description, geometry, dense M / K (dim^2 doubles each; 63 x 63 = 31 KB: L2-resident) and state
 // vectors live in one device arena; `Body` views (pointers into it) sit in a device array indexed by blockIdx.x.  The marker
@@ -97,8 +98,20 @@ using namespace life;
 
 extern "C" {
 
+static int fem_create_impl(life_ctx *ctx, int32_t n_bodies, const life_fem_body *desc);
+
 int life_fem_create(life_ctx *ctx, int32_t n_bodies, const life_fem_body *desc) {
 	if (!ctx) return LIFE_E_ARG;
+	const int rc = fem_create_impl(ctx, n_bodies, desc);
+	if (rc != LIFE_OK) {      // never leave a half-built set behind: later life_fem_* calls must fail with LIFE_E_STATE, not fault
+		const std::string msg = ctx->err;
+		fem_free(ctx);
+		ctx->err = msg;
+	}
+	return rc;
+}
+
+static int fem_create_impl(life_ctx *ctx, int32_t n_bodies, const life_fem_body *desc) {
 	if (n_bodies < 0 || (n_bodies > 0 && !desc)) return fail(ctx, LIFE_E_ARG, "life_fem_create: null description");
 	LIFE_CUDA(ctx, cudaSetDevice(ctx->device));
 	LIFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -1,11 +1,10 @@
 // fem_core.h — the structural solver of one flexible body as cooperative-thread-array code.
 //
-// STATUS: prepared component, NOT yet compiled into liblife_b200.so.  The same source is meant to run as one CTA per filament on
-// the device (every loop strides by the CTA size, phases are separated by FEM_SYNC) and, with a CTA of one thread and FEM_SYNC a
-// no-op, serially on the host.  The serial instantiation is what tests/test_fem_core.py holds against the compiled reference
-// today (logic, operation by operation); the barrier placement is checked on the host as well, by running the CTA as real
-// threads with FEM_SYNC a pthread barrier under ThreadSanitizer (tests/native/fem_core_race.cpp).  What remains before this is
-// wired to the ABI is the run on a B200.
+// The same source runs as one CTA per filament on the device (csrc/fem.cu: every loop strides by the CTA size, phases are separated
+// by FEM_SYNC) and, with a CTA of one thread and FEM_SYNC a no-op, serially on the host.  The serial instantiation is what
+// tests/test_fem_core.py holds against the compiled reference (logic, operation by operation); the barrier placement is checked
+// on the host as well, by running the CTA as real threads with FEM_SYNC a pthread barrier under ThreadSanitizer
+// (tests/native/fem_core_race.cpp); the device instantiation by tests/test_gpu_fem.py on a B200.
 //
 // What it computes, per body and sub-iteration (reference: FEMBodyClass, src/FEMBody.cpp / FEMElementClass, src/FEMElement.cpp):
 //   fem_dynamic   dynamicFEM (src/FEMBody.cpp:26-68): U := U_n; load vector from the marker forces (loadVector, src/FEMElement.cpp:27-69);

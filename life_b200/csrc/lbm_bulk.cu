@@ -377,11 +377,8 @@ __global__ void __launch_bounds__(256, 2) k_bulk_tma(const BulkArgs a, const int
 
 template <int COLL, int MODE>
 static int launch_tma(life_ctx *ctx, BulkArgs a, int64_t c_count, cudaStream_t st) {
-	static bool configured = false;    // per template instance
-	if (!configured) {
-		LIFE_CUDA(ctx, cudaFuncSetAttribute(k_bulk_tma<COLL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM_BYTES));
-		configured = true;
-	}
+	// per launch: the attribute is per device, and one process may hold contexts on several GPUs (cheap: no synchronisation)
+	LIFE_CUDA(ctx, cudaFuncSetAttribute(k_bulk_tma<COLL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM_BYTES));
 	a.tiles = (a.L.Ny + TMA_TILE - 1) / TMA_TILE;
 	const int64_t n_tiles = a.tiles * c_count;
 	if (n_tiles <= 0) return LIFE_OK;

@@ -538,8 +538,19 @@ int start_job(life_ctx *ctx, FileJob &job, int mode) {
 	int rc = ensure_io(ctx);
 	if (rc) return rc;
 	if ((rc = io_wait(ctx))) return rc;   // completes (and reports) the previous asynchronous write
-	if ((rc = ensure_staging(ctx))) return rc;
 	IoState *io = ctx->io;
+	// A rank that fails before its job exists must still take part in the collective completion (io_wait's status exchange), or the
+	// other ranks would wait for it forever: it enters the exchange with its error and everybody returns one.
+	auto early = [&](int code) {
+		if (!ctx->comm) return code;
+		io->job = job;
+		io->rc = code;
+		io->err = ctx->err;
+		io->pending = true;
+		io->finished.store(true, std::memory_order_relaxed);
+		return io_wait(ctx);
+	};
+	if ((rc = ensure_staging(ctx))) return early(rc);
 	const Layout &L = ctx->L;
 	const size_t S = (size_t)L.S;
 
@@ -561,7 +572,7 @@ int start_job(life_ctx *ctx, FileJob &job, int mode) {
 		if (ctx->stored_macro_valid) {
 			LIFE_CUDA(ctx, cudaMemcpyAsync(snap, ctx->macro, sizeof(double) * 3 * S, cudaMemcpyDeviceToDevice, ctx->stream));
 		} else if ((rc = launch_macro(ctx, snap, 0, L.nxl))) {
-			return rc;
+			return early(rc);
 		}
 		job.stored = snap;
 		if (restart) {
@@ -599,12 +610,17 @@ int start_job(life_ctx *ctx, FileJob &job, int mode) {
 
 }  // namespace
 
-// all ranks have reached this point (a one-element all-reduce on the compute stream, then a host wait)
-static int comm_barrier(life_ctx *ctx) {
+// All ranks have reached this point AND know whether any of them failed: a one-element max all-reduce of each rank's status on the
+// compute stream, then a host wait.  *any receives the largest status (0 = every rank is fine).
+static int comm_agree(life_ctx *ctx, int mine, int *any) {
 	if (!ctx->d_red) LIFE_CUDA(ctx, cudaMalloc(&ctx->d_red, 64));
-	LIFE_CUDA(ctx, cudaMemsetAsync(ctx->d_red + 4, 0, sizeof(double), ctx->stream));
-	LIFE_NCCL(ctx, ncclAllReduce(ctx->d_red + 4, ctx->d_red + 4, 1, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+	double *h = reinterpret_cast<double *>(ctx->h_pin) + 8;
+	*h = mine != LIFE_OK ? 1.0 : 0.0;
+	LIFE_CUDA(ctx, cudaMemcpyAsync(ctx->d_red + 4, h, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+	LIFE_NCCL(ctx, ncclAllReduce(ctx->d_red + 4, ctx->d_red + 4, 1, ncclDouble, ncclMax, ctx->comm, ctx->stream));
+	LIFE_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_red + 4, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
 	LIFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	*any = *h != 0.0 ? 1 : 0;
 	return LIFE_OK;
 }
 
@@ -617,16 +633,24 @@ int io_wait(life_ctx *ctx) {
 	int rc = io->rc;
 	std::string err = io->err;
 	if (ctx->comm) {
-		// every rank's bytes must be in the file before rank 0 renames it, and the rename must have happened before any rank
-		// goes on (to read the file back, or to open the next .temp)
-		int brc = comm_barrier(ctx);
+		// Every rank's bytes must be in the file before rank 0 renames it — and the rename must not happen at all if ANY rank failed
+		// (a truncated .temp must never replace the last good restart file): the first exchange carries every rank's status.
+		// The rename must have happened before any rank goes on (to read the file back, or to open the next .temp): second exchange,
+		// which also spreads a failed rename.
+		int any = 0;
+		int brc = comm_agree(ctx, rc, &any);
 		if (brc) return brc;
-		if (rc == LIFE_OK && io->job.kind == JOB_RESTART && ctx->cfg.rank == 0 &&
+		if (any == 0 && io->job.kind == JOB_RESTART && ctx->cfg.rank == 0 &&
 		    rename(io->job.path.c_str(), io->job.final_path.c_str()) != 0) {
 			rc = LIFE_E_IO;
 			err = "rename " + io->job.path + ": " + strerror(errno);
 		}
-		if ((brc = comm_barrier(ctx))) return brc;
+		int any2 = 0;
+		if ((brc = comm_agree(ctx, rc, &any2))) return brc;
+		if (rc == LIFE_OK && (any || any2)) {
+			rc = LIFE_E_IO;
+			err = "file output failed on another rank; " + (io->job.kind == JOB_RESTART ? "the previous " + io->job.final_path + " was kept" : io->job.path + " is incomplete");
+		}
 	}
 	if (rc) return fail(ctx, rc, err);
 	return LIFE_OK;

@@ -17,11 +17,11 @@ OBJ = os.path.join(HERE, "lib", "obj")
 LIB = os.path.join(HERE, "lib", "liblife_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
-SOURCES = ["api.cu", "lbm_bulk.cu", "lbm_boundary.cu", "lbm_io.cu", "lbm_file.cu", "halo.cu", "ibm.cu", "ibm_eps.cu", "fem.cu", "nccl_dyn.cu", "membw.cu"]
+SOURCES = ["api.cu", "lbm_bulk.cu", "lbm_boundary.cu", "lbm_io.cu", "lbm_file.cu", "halo.cu", "ibm.cu", "ibm_eps.cu", "fem.cu", "nccl_dyn.cu", "membw.cu", "lbm_small.cu"]
 # second compilation of the step kernels in the reference's operation order (cfg.exact): no FMA contraction, namespace life::exact
 EXACT_FLAGS = ["-DLIFE_EXACT", "-fmad=false"]
 VARIANTS = [(s, s.replace(".cu", ".o"), []) for s in SOURCES] + \
-           [(s, s.replace(".cu", "_exact.o"), EXACT_FLAGS) for s in ("lbm_bulk.cu", "lbm_boundary.cu")]
+           [(s, s.replace(".cu", "_exact.o"), EXACT_FLAGS) for s in ("lbm_bulk.cu", "lbm_boundary.cu", "lbm_small.cu")]
 
 NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 # sm_100a only (B200); -lineinfo so ncu's source page maps to these files.  The host compiler is the system g++.

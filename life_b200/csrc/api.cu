@@ -53,7 +53,9 @@ static void free_ctx(life_ctx *ctx) {
 	if (ctx->comm) ncclCommDestroy(ctx->comm);
 	cudaFree(ctx->fA); cudaFree(ctx->fB); cudaFree(ctx->macro); cudaFree(ctx->fibm); cudaFree(ctx->fibm_mask); cudaFree(ctx->fxyf);
 	cudaFree(ctx->cell_head); cudaFree(ctx->u_in); cudaFree(ctx->rho_in); cudaFree(ctx->delU); cudaFree(ctx->bc);
-	cudaFree(ctx->scratch); cudaFree(ctx->d_red); cudaFree(ctx->eps_buf);
+	cudaFree(ctx->scratch); cudaFree(ctx->d_red); cudaFree(ctx->eps_buf); cudaFree(ctx->d_steps);
+	if (ctx->h_steps) cudaFreeHost(ctx->h_steps);
+	if (ctx->ev_steps) cudaEventDestroy(ctx->ev_steps);
 	if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
 	for (auto &p : ctx->prof_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
 	if (ctx->ev_edge) cudaEventDestroy(ctx->ev_edge);
@@ -457,10 +459,52 @@ int life_step(life_ctx *ctx, int32_t t) {
 	return LIFE_OK;
 }
 
+// lattices up to this many nodes step faster inside one 8-SM cluster launch than through launch-bound per-step kernels (lbm_small.cu)
+static constexpr int64_t SMALL_MAX_NODES = 65536;
+static constexpr int32_t SMALL_MAX_STEPS = 1024;   // per launch
+
+static bool small_path(const life_ctx *ctx) {
+	if (ctx->cfg.tune == 30) return false;          // measurement: per-step launches only
+	return ctx->cfg.nranks <= 1 && !ctx->fibm_any && ctx->fxy_mode != life::FXY_FIELD && !ctx->stored_macro_valid && !ctx->profiling &&
+	       ctx->L.nxl * ctx->L.Ny <= SMALL_MAX_NODES;
+}
+
 int life_step_n(life_ctx *ctx, int32_t t_first, int32_t n) {
-	for (int32_t k = 0; k < n; k++) {
-		int rc = life_step(ctx, t_first + k);
+	if (!ctx) return LIFE_E_ARG;
+	int32_t k = 0;
+	while (k < n) {
+		if (n - k < 2 || !small_path(ctx)) {       // (the first step after an upload carries stored macroscopics: per-step path)
+			int rc = life_step(ctx, t_first + k);
+			if (rc) return rc;
+			k++;
+			continue;
+		}
+		// the remaining steps, up to SMALL_MAX_STEPS at a time, in one launch
+		if (!ctx->have_state) return fail(ctx, LIFE_E_STATE, "life_step_n: no state uploaded");
+		LIFE_CUDA(ctx, cudaSetDevice(ctx->device));
+		const int32_t m = n - k < SMALL_MAX_STEPS ? n - k : SMALL_MAX_STEPS;
+		if (!ctx->d_steps) {
+			LIFE_CUDA(ctx, cudaMalloc(&ctx->d_steps, sizeof(StepScalars) * SMALL_MAX_STEPS));
+			LIFE_CUDA(ctx, cudaMallocHost(&ctx->h_steps, sizeof(StepScalars) * SMALL_MAX_STEPS));
+			LIFE_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_steps, cudaEventDisableTiming));
+			ctx->steps_cap = SMALL_MAX_STEPS;
+		} else {
+			LIFE_CUDA(ctx, cudaEventSynchronize(ctx->ev_steps));     // the previous batch's scalars have left the pinned buffer
+		}
+		for (int32_t q = 0; q < m; q++) {
+			// the uniform force a step sees as "previous" is the one the step before it applied (Womersley: it changes every step)
+			ctx->h_steps[q] = step_scalars(ctx, t_first + k + q);
+			ctx->fxy_uniform[0] = ctx->h_steps[q].fxy_cur[0];
+			ctx->fxy_uniform[1] = ctx->h_steps[q].fxy_cur[1];
+		}
+		LIFE_CUDA(ctx, cudaMemcpyAsync(ctx->d_steps, ctx->h_steps, sizeof(StepScalars) * m, cudaMemcpyHostToDevice, ctx->stream));
+		LIFE_CUDA(ctx, cudaEventRecord(ctx->ev_steps, ctx->stream));
+		int rc = ctx->cfg.exact ? launch_steps_small_exact(ctx, ctx->d_steps, ctx->h_steps[0], m) : launch_steps_small(ctx, ctx->d_steps, ctx->h_steps[0], m);
 		if (rc) return rc;
+		if (m & 1) { double *tmp = ctx->fA; ctx->fA = ctx->fB; ctx->fB = tmp; }
+		ctx->fibm_consumed = true;
+		ctx->last_t = t_first + k + m - 1;
+		k += m;
 	}
 	return LIFE_OK;
 }

@@ -120,6 +120,9 @@ struct life_ctx {
 	double *scratch = nullptr;            // device staging for upload / download
 	size_t scratch_bytes = 0;
 	double *d_red = nullptr;              // reduction scratch (max speed etc.)
+	life::StepScalars *d_steps = nullptr, *h_steps = nullptr;   // per-step scalars of a multi-step launch (lbm_small.cu): device + pinned host
+	int32_t steps_cap = 0;
+	cudaEvent_t ev_steps = nullptr;       // the last upload out of h_steps has completed
 	void *eps_buf = nullptr;              // epsilon assembly / LU scratch (ibm_eps.cu)
 	size_t eps_bytes = 0;
 	void *h_pin = nullptr;                // small pinned host buffer
@@ -153,6 +156,9 @@ int fail(life_ctx *ctx, int code, const std::string &msg);
 // lbm_bulk.cu
 int launch_bulk(life_ctx *ctx, const StepScalars &sc, int64_t c_first, int64_t c_count, cudaStream_t st);
 int launch_bulk_exact(life_ctx *ctx, const StepScalars &sc, int64_t c_first, int64_t c_count, cudaStream_t st);   // cfg.exact
+// lbm_small.cu: n steps of a small single-rank lattice in one launch of one thread-block cluster (d_sc: per-step scalars on the device)
+int launch_steps_small(life_ctx *ctx, const StepScalars *d_sc, const StepScalars &first, int n);
+int launch_steps_small_exact(life_ctx *ctx, const StepScalars *d_sc, const StepScalars &first, int n);
 // lbm_boundary.cu
 int build_boundary(life_ctx *ctx);
 int launch_convective_speed(life_ctx *ctx, const StepScalars &sc);

@@ -77,6 +77,7 @@ struct DeviceSide {
 	double t_info = 0, t_vtk = 0, t_restart = 0;   // parts of t_io
 	double t_fem = 0;   // inside the optional device FEM bindings
 	long fem_calls = 0;
+	int deferred = 0, deferred_first = 0;   // body-free cases: time steps not yet handed to the library (flush_steps)
 	double t_object = 0;   // inside ObjectsClass::objectKernel (whichever implementation runs it)
 	long sub_its = 0;
 } dev;
@@ -156,8 +157,10 @@ life_config make_config(const GridClass &g) {
 	return c;
 }
 
+void flush_steps();
 void report() {
 	if (!dev.ctx || team.abandon) return;
+	flush_steps();
 	ON_ALL_RANKS(r, life_sync(dev.ctxs[r]));
 	bool io_failed = false;
 	ON_ALL_RANKS(r, if (life_io_wait(dev.ctxs[r]) != LIFE_OK) io_failed = true);   // the last asynchronous file write (collective)
@@ -246,12 +249,29 @@ void ensure_state(GridClass &g) {
 }  // namespace
 
 // ---- GridClass::lbmKernel -------------------------------------------------------------------------------------------------------
+namespace {
+// Without bodies nothing observes the lattice between output calls, so consecutive steps are handed over together: life_step_n runs
+// them in ONE launch for small lattices (csrc/lbm_small.cu), instead of 2-4 launch-bound kernels per step.
+void flush_steps() {
+	if (dev.deferred == 0) return;
+	Timed timed(dev.t_step);
+	const int t0 = dev.deferred_first, n = dev.deferred;
+	dev.deferred = 0;
+	ON_ALL_RANKS(r, LIFE_CK(life_step_n(dev.ctxs[(size_t)r], t0, n)));
+}
+}  // namespace
+
 void GridClass::lbmKernel() {
 	ensure_state(*this);   // first step of a run whose output goes through the host mirrors, or of a restart read on the host
-	Timed timed(dev.t_step);
-	ON_ALL_RANKS(r, LIFE_CK(life_step(dev.ctxs[(size_t)r], t)));
 	dev.steps++;
 	dev.macro_stale = dev.full_stale = true;
+	if (!oPtr->hasIBM && dev.nranks == 1) {      // deferred: flushed by the next call that looks at the state (writeInfo / writeVTK / writeRestart / exit)
+		if (dev.deferred == 0) dev.deferred_first = t;
+		dev.deferred++;
+		return;
+	}
+	Timed timed(dev.t_step);
+	ON_ALL_RANKS(r, LIFE_CK(life_step(dev.ctxs[(size_t)r], t)));
 }
 
 namespace {
@@ -612,6 +632,7 @@ void ObjectsClass::ibmKernelSpread() {
 
 // ---- output and restart: device-fed by default, through the host mirrors with LIFE_B200_HOST_IO=1 -------------------------------------
 void GridClass::writeInfo() {
+	flush_steps();
 	if (oPtr && oPtr->hasFlex) fem_refresh_all(*oPtr);      // the resident sub-iteration loop leaves the host's body state behind
 
 	if (!host_io()) ensure_state(*this);
@@ -656,6 +677,7 @@ void GridClass::writeInfo() {
 }
 
 void GridClass::writeVTK() {
+	flush_steps();
 	if (oPtr && oPtr->hasFlex) fem_refresh_all(*oPtr);      // the resident sub-iteration loop leaves the host's body state behind
 
 	if (!(host_io() || bigEndian)) ensure_state(*this);
@@ -687,6 +709,7 @@ void GridClass::writeVTK() {
 }
 
 void GridClass::writeRestart() {
+	flush_steps();
 	if (oPtr && oPtr->hasFlex) fem_refresh_all(*oPtr);      // the resident sub-iteration loop leaves the host's body state behind
 
 	if (!(host_io() || bigEndian)) ensure_state(*this);

@@ -118,6 +118,42 @@ def test_kernel_variants_agree_bit_for_bit(setup, collision):
         assert K.rel_l2(out[4][name], o.get(name)) < K.TOL, name
 
 
+@pytest.mark.parametrize("exact", [0, 1], ids=["fast", "exact"])
+@pytest.mark.parametrize("case", K.EXAMPLES_LBM + K.EXTRA)
+def test_persistent_small_lattice_kernel_is_bitwise_the_per_step_path(case, exact):
+    """life_step_n on a small lattice runs all steps inside ONE launch of one thread-block cluster (csrc/lbm_small.cu: phases separated
+    by the cluster barrier instead of kernel boundaries).  Same per-node device code as the per-step kernels, so the state after N
+    steps must be identical bit for bit — for every boundary type, periodic wrap, Womersley forcing, convective outlet, both
+    collision operators, default and exact arithmetic — and the launch count must show the single launch."""
+    from life_b200 import capi
+    g = K.golden(case)
+    o = K.make_oracle(g)
+    N = int(g["steps"])
+    a = capi.Context(K.life_config(o.params, o, exact=exact, tune=30))      # tune 30: per-step launches only
+    K.upload_from_oracle(a, o)
+    for t in range(1, N + 1):
+        a.step(t)
+    b = capi.Context(K.life_config(o.params, o, exact=exact))
+    K.upload_from_oracle(b, o)
+    n0 = b.launch_count()
+    b.step_n(1, N)
+    launches = b.launch_count() - n0
+    sa, sb = a.download_state(), b.download_state()
+    for name in ("f", "rho", "u"):
+        assert np.array_equal(sa[name], sb[name]), (case, name, K.rel_l2(sb[name], sa[name]))
+    # first step (stored macroscopics of the upload) through the per-step path, the other N-1 in one launch
+    per_step = (a.launch_count()) // N
+    assert launches <= per_step + 3, (launches, per_step)
+    # and it continues correctly: more steps in a second batch, odd count (buffer parity)
+    for t in range(N + 1, N + 8):
+        a.step(t)
+    b.step_n(N + 1, 7)
+    sa, sb = a.download_state(), b.download_state()
+    assert np.array_equal(sa["f"], sb["f"])
+    a.close()
+    b.close()
+
+
 def test_restart_roundtrip_is_transparent():
     """download_state -> upload_state in the middle of a run must not change the trajectory (restart files,
     src/Grid.cpp:1072-1229, carry exactly these arrays)."""

@@ -460,7 +460,7 @@ int life_step(life_ctx *ctx, int32_t t) {
 }
 
 // lattices up to this many nodes step faster inside one 8-SM cluster launch than through launch-bound per-step kernels (lbm_small.cu)
-static constexpr int64_t SMALL_MAX_NODES = 65536;
+static constexpr int64_t SMALL_MAX_NODES = 16384;
 static constexpr int32_t SMALL_MAX_STEPS = 1024;   // per launch
 
 static bool small_path(const life_ctx *ctx) {

@@ -7,9 +7,12 @@
 // the phases of a step — [outlet speed] -> sweep -> ghost ring -> boundary nodes — are separated by the cluster's hardware barrier
 // (barrier.cluster, release / acquire at cluster scope: the populations live in global memory, i.e. in L2, and become visible to
 // the other CTAs of the cluster across the barrier) instead of by kernel boundaries.  The per-node arithmetic is the sweep's and
-// the boundary kernel's own device code (lbm_bulk.cuh, lbm_boundary.cuh), so results are bit-identical to stepping with
-// life_step, in the default and in the exact build (this file is compiled twice like they are).
+// the boundary kernel's own device code (lbm_bulk.cuh, lbm_boundary.cuh; this file is compiled twice like they are): in the exact
+// build results are bit-identical to stepping with life_step, in the default build identical up to which product of an a*b + c*d the
+// compiler contracts into the FMA (rounding level).
 //
+// Measured (profiles/r02_small_lattice_timing.txt): LidDrivenCavity 9.4 us/step against 10.2 with per-step launches, fully periodic
+// 40 x 36: 7.4 against 26 (the per-step path needs 5+ launches there); above ~16 k nodes the 8 SMs lose to the whole-GPU kernels.
 // Used by life_step_n (api.cu) when the lattice is small enough for 8 SMs to beat the launch-bound path (<= SMALL_MAX_NODES), there
 // is one rank, no force field and no stored macroscopics; everything else takes the per-step path.
 #include "ctx.h"

@@ -95,7 +95,12 @@ typedef struct life_config {
 	                              :387-495) — so that fields, marker forces and files equal the reference's g++ build bit for bit (the
 	                              reference's own regression protocol is `diff -r`, testing/run-tests.sh:100).  ~3x the arithmetic of the
 	                              default factored collision.  Central moments: same factored form, FMA-free (deterministic, not bitwise). */
-	int32_t reserved[5];
+	int32_t inplace;           /* 1: ONE population buffer (72 B/node resident instead of 144): the sweep collides in place and streaming is
+	                              implicit — population v of node n lives at plane element (n - t_steps * shift_v) mod S, shift_v = cx * pitch + cy,
+	                              so "pushing" it to its neighbour is an offset update, not a data movement (csrc/lbm_bulk.cu: k_bulk_shift).
+	                              Same results, same 144 B/node of traffic per step; every state-returning call still delivers the
+	                              reference convention.  32768^2 then needs 77 GB and leaves room for the asynchronous restart snapshot. */
+	int32_t reserved[4];
 } life_config;
 
 typedef struct life_ctx life_ctx;

@@ -50,7 +50,7 @@ class Config(C.Structure):
                 ("stream", C.c_void_p),
                 ("rank", C.c_int32), ("nranks", C.c_int32),
                 ("nccl_id", C.c_void_p),
-                ("kernel", C.c_int32), ("tune", C.c_int32), ("exact", C.c_int32), ("reserved", C.c_int32 * 5)]
+                ("kernel", C.c_int32), ("tune", C.c_int32), ("exact", C.c_int32), ("inplace", C.c_int32), ("reserved", C.c_int32 * 4)]
 
     def __init__(self, **kw):
         super().__init__()

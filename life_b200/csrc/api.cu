@@ -51,6 +51,7 @@ static void free_ctx(life_ctx *ctx) {
 	fem_free(ctx);
 	ibm_free(ctx);
 	if (ctx->comm) ncclCommDestroy(ctx->comm);
+	cudaFree(ctx->bc_prev); cudaFree(ctx->halo_buf);
 	cudaFree(ctx->fA); cudaFree(ctx->fB); cudaFree(ctx->macro); cudaFree(ctx->fibm); cudaFree(ctx->fibm_mask); cudaFree(ctx->fxyf);
 	cudaFree(ctx->cell_head); cudaFree(ctx->u_in); cudaFree(ctx->rho_in); cudaFree(ctx->delU); cudaFree(ctx->bc);
 	cudaFree(ctx->scratch); cudaFree(ctx->d_red); cudaFree(ctx->eps_buf); cudaFree(ctx->d_steps);
@@ -154,10 +155,13 @@ int life_create(const life_config *cfg, life_ctx **out) {
 	// + 64 doubles: the last warp of a column loads its full 64-row span even when the column ends inside it (lbm_bulk.cu), which
 	// for tiny Ny (pitch < 64 rows) reaches past the ghost column of the last plane
 	const size_t fbytes = sizeof(double) * (9 * (size_t)L.S + 64);
+	ctx->inplace = cfg->inplace != 0;
 	CK(cudaMalloc(&ctx->fA, fbytes));
-	CK(cudaMalloc(&ctx->fB, fbytes));
 	CK(cudaMemsetAsync(ctx->fA, 0, fbytes, ctx->stream));
-	CK(cudaMemsetAsync(ctx->fB, 0, fbytes, ctx->stream));
+	if (!ctx->inplace) {      // cfg.inplace: one buffer, 72 B/node
+		CK(cudaMalloc(&ctx->fB, fbytes));
+		CK(cudaMemsetAsync(ctx->fB, 0, fbytes, ctx->stream));
+	}
 	CK(cudaMalloc(&ctx->u_in, sizeof(double) * 2 * L.Ny));
 	CK(cudaMalloc(&ctx->rho_in, sizeof(double) * L.Ny));
 	CK(cudaMalloc(&ctx->delU, sizeof(double) * 2 * L.Ny));
@@ -213,6 +217,7 @@ int life_upload_begin(life_ctx *ctx, const double *u_in, const double *rho_in) {
 	LIFE_CUDA(ctx, cudaSetDevice(ctx->device));
 	const Layout &L = ctx->L;
 	ctx->have_state = false;
+	ctx->shift = PopShift{};              // an upload delivers the plain layout
 	ctx->uploading = true;
 	ctx->up_macro = -1;
 	ctx->up_cols = 0;
@@ -360,7 +365,7 @@ int life_download_columns(life_ctx *ctx, int64_t il0, int64_t ncols, double *f, 
 	if (ncols == 0) return LIFE_OK;
 	LIFE_CUDA(ctx, cudaSetDevice(ctx->device));
 	int rc;
-	if (f && (rc = download_field(ctx, f, ctx->fA, 9, il0, ncols))) return rc;
+	if (f && (rc = download_field(ctx, f, ctx->fA, 9, il0, ncols, &ctx->shift))) return rc;
 	if (rho || u) {
 		if (!ctx->stored_macro_valid) {   // otherwise `macro` already holds exactly what the host uploaded
 			if ((rc = ensure_macro(ctx))) return rc;
@@ -412,6 +417,17 @@ int life_step(life_ctx *ctx, int32_t t) {
 	// cfg.exact selects the kernels compiled in the reference's operation order without FMA contraction (namespace life::exact)
 	const bool exact = ctx->cfg.exact != 0;
 	auto bulk = exact ? launch_bulk_exact : launch_bulk;
+	// cfg.inplace: what the boundary kernel needs of the pre-sweep state is saved first; after the sweep the layout offsets advance
+	// (that is the streaming), and ring / halo / boundary work on the advanced layout of the same buffer
+	if (ctx->inplace && (rc = exact ? launch_bc_capture_exact(ctx, sc) : launch_bc_capture(ctx, sc))) return rc;
+	auto advance = [&]() {
+		if (!ctx->inplace) return;
+		static const int cx[9] = {0, 1, -1, 0, 0, 1, -1, 1, -1}, cy[9] = {0, 0, 0, 1, -1, 1, -1, -1, 1};
+		for (int v = 0; v < 9; v++) {
+			int64_t o = (ctx->shift.off[v] + cx[v] * L.P + cy[v]) % L.S;
+			ctx->shift.off[v] = o < 0 ? o + L.S : o;
+		}
+	};
 	if ((rc = exact ? launch_convective_speed_exact(ctx, sc) : launch_convective_speed(ctx, sc))) return rc;
 
 	cudaEvent_t p0 = nullptr, p1 = nullptr;
@@ -431,26 +447,36 @@ int life_step(life_ctx *ctx, int32_t t) {
 		if (p0) LIFE_CUDA(ctx, cudaEventRecord(p0, ctx->stream));
 		if ((rc = bulk(ctx, sc, 1, L.nxl, ctx->stream))) return rc;
 		if (p1) LIFE_CUDA(ctx, cudaEventRecord(p1, ctx->stream));
+		advance();
 		if ((rc = launch_wrap_y(ctx, ctx->stream, false))) return rc;
 		if ((rc = exchange_x(ctx))) return rc;
 	} else {
 		// the two edge columns first, so their ghost columns can travel while the interior is swept
+		// (cfg.inplace: the sweeps address the buffer through the layout before the step, ring / halo / boundary through the advanced
+		// one; kernel arguments are taken at launch, so ctx->shift is switched back and forth around the launches)
+		const PopShift before = ctx->shift;
+		advance();
+		const PopShift after = ctx->shift;
+		ctx->shift = before;
 		if ((rc = bulk(ctx, sc, 1, 1, ctx->stream))) return rc;
 		if ((rc = bulk(ctx, sc, L.nxl, 1, ctx->stream))) return rc;
+		ctx->shift = after;
 		if ((rc = launch_wrap_y(ctx, ctx->stream, false))) return rc;   // ring corners of the ghost columns
 		LIFE_CUDA(ctx, cudaEventRecord(ctx->ev_edge, ctx->stream));
 		LIFE_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_edge, 0));
 		if ((rc = exchange_x(ctx))) return rc;
 		LIFE_CUDA(ctx, cudaEventRecord(ctx->ev_comm, ctx->comm_stream));
 		if (p0) LIFE_CUDA(ctx, cudaEventRecord(p0, ctx->stream));
+		ctx->shift = before;
 		if ((rc = bulk(ctx, sc, 2, L.nxl - 2, ctx->stream))) return rc;
+		ctx->shift = after;
 		if (p1) LIFE_CUDA(ctx, cudaEventRecord(p1, ctx->stream));
 		if ((rc = launch_wrap_y(ctx, ctx->stream, true))) return rc;    // what the interior sweep pushed over the top/bottom
 		LIFE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));
 	}
 	if ((rc = exact ? launch_boundary_exact(ctx, sc) : launch_boundary(ctx, sc))) return rc;
 
-	double *tmp = ctx->fA; ctx->fA = ctx->fB; ctx->fB = tmp;
+	if (!ctx->inplace) { double *tmp = ctx->fA; ctx->fA = ctx->fB; ctx->fB = tmp; }
 	ctx->stored_macro_valid = false;
 	ctx->fibm_consumed = true;
 	ctx->fxy_uniform[0] = sc.fxy_cur[0];
@@ -465,7 +491,7 @@ static constexpr int32_t SMALL_MAX_STEPS = 1024;   // per launch
 
 static bool small_path(const life_ctx *ctx) {
 	if (ctx->cfg.tune == 30) return false;          // measurement: per-step launches only
-	return ctx->cfg.nranks <= 1 && !ctx->fibm_any && ctx->fxy_mode != life::FXY_FIELD && !ctx->stored_macro_valid && !ctx->profiling &&
+	return ctx->cfg.nranks <= 1 && !ctx->inplace && !ctx->fibm_any && ctx->fxy_mode != life::FXY_FIELD && !ctx->stored_macro_valid && !ctx->profiling &&
 	       ctx->L.nxl * ctx->L.Ny <= SMALL_MAX_NODES;
 }
 

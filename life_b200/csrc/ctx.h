@@ -31,6 +31,17 @@ struct Layout {
 	__host__ __device__ int64_t node(int64_t il, int64_t j) const { return (il + 1) * P + (j + JOFF); }
 };
 
+// In-place ("shift") layout of the population planes (cfg.inplace): population v of logical element idx sits at plane element
+// (idx - off[v]) mod S; off[v] grows by shift_v = cx*P + cy every step, which IS the streaming.  All zero = the plain layout, so
+// every kernel that is not on the hot path of the two-buffer sweep addresses populations through at().
+struct PopShift {
+	int64_t off[9];
+	__host__ __device__ __forceinline__ int64_t at(int v, int64_t idx, int64_t S) const {
+		const int64_t i = idx - off[v];
+		return v * S + (i < 0 ? i + S : i);
+	}
+};
+
 // one boundary node (element of BCVec, src/Grid.cpp:947-949) with its normal precomputed (src/Grid.cpp:498-545)
 struct BcNode {
 	int32_t il;      // local column index
@@ -82,7 +93,11 @@ struct life_ctx {
 	int64_t i_begin = 0, i_end = 0;       // global columns owned
 	life::Layout L{};
 
-	double *fA = nullptr, *fB = nullptr;  // population buffers, 9 planes each; fA holds the current state
+	double *fA = nullptr, *fB = nullptr;  // population buffers, 9 planes each; fA holds the current state (cfg.inplace: fB stays null)
+	bool inplace = false;
+	life::PopShift shift{};               // where the populations of fA sit (all zero unless cfg.inplace)
+	double *halo_buf = nullptr;           // cfg.inplace, nranks > 1: contiguous send / receive staging of the two faces, 4 * 3 * Ny doubles
+	double *bc_prev = nullptr;            // cfg.inplace: what the boundary kernel needs of the state BEFORE the sweep, 3 doubles per BCVec entry
 	double *macro = nullptr;              // rho, ux, uy planes (3*S), lazily allocated
 	double *fibm = nullptr;               // force_ibm planes (2*S), lazily allocated
 	uint8_t *fibm_mask = nullptr;         // one byte per (column, 64-row span): 1 where a spread has written force_ibm.  Exact while
@@ -164,13 +179,15 @@ int build_boundary(life_ctx *ctx);
 int launch_convective_speed(life_ctx *ctx, const StepScalars &sc);
 int launch_wrap_y(life_ctx *ctx, cudaStream_t st, bool after_exchange);
 int launch_boundary(life_ctx *ctx, const StepScalars &sc);
+int launch_bc_capture(life_ctx *ctx, const StepScalars &sc);     // cfg.inplace: before the sweep
 int launch_convective_speed_exact(life_ctx *ctx, const StepScalars &sc);   // cfg.exact: the same two in the reference's operation order
 int launch_boundary_exact(life_ctx *ctx, const StepScalars &sc);
+int launch_bc_capture_exact(life_ctx *ctx, const StepScalars &sc);
 // halo.cu
 int exchange_x(life_ctx *ctx);
 // lbm_io.cu
 int upload_field(life_ctx *ctx, const double *h, double *planes, int ncomp, int64_t il0, int64_t ncols);
-int download_field(life_ctx *ctx, double *h, const double *planes, int ncomp, int64_t il0, int64_t ncols);
+int download_field(life_ctx *ctx, double *h, const double *planes, int ncomp, int64_t il0, int64_t ncols, const PopShift *ps = nullptr);
 int fill_field(life_ctx *ctx, double *planes, int ncomp, int64_t il0, int64_t ncols, double v0, double v1);
 int launch_macro(life_ctx *ctx, double *out_planes, int64_t il0, int64_t ncols);
 int launch_max_speed(life_ctx *ctx, double *vmax, int32_t *has_nan, int64_t *nan_id);

@@ -236,6 +236,7 @@ int ibm_check(life_ctx *ctx) {
 struct InterpArgs {
 	int64_t n;
 	const double *f;
+	PopShift ps;
 	Layout L;
 	int64_t i_begin;
 	int fxy_mode;
@@ -261,7 +262,7 @@ __global__ void __launch_bounds__(128) k_interp(const InterpArgs a) {
 			// rho, u as GridClass::macroscopic left them (src/Grid.cpp:282-299): no IBM force at this point of the step
 			double p[NV], rho, mx, my;
 #pragma unroll
-			for (int v = 0; v < NV; v++) p[v] = a.f[v * a.L.S + idx];
+			for (int v = 0; v < NV; v++) p[v] = a.f[a.ps.at(v, idx, a.L.S)];
 			moments(p, rho, mx, my);
 			double fx = a.fx, fy = a.fy;
 			if (a.fxy_mode == FXY_FIELD) { fx = a.fxyf[idx]; fy = a.fxyf[a.L.S + idx]; }
@@ -310,6 +311,7 @@ int ibm_interp(life_ctx *ctx, double *force_out, bool no_sync) {
 	InterpArgs a{};
 	a.n = m.n;
 	a.f = ctx->fA;
+	a.ps = ctx->shift;
 	a.L = ctx->L;
 	a.i_begin = ctx->i_begin;
 	a.fxy_mode = ctx->fxy_mode;

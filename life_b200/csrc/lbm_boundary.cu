@@ -81,17 +81,17 @@ int build_boundary(life_ctx *ctx) {
 // `after_exchange` = second pass of a multi-rank step (after the interior sweep, concurrent with the halo receive): it must
 // leave alone what the x exchange delivers — the cx = +1 planes of the first column, the cx = -1 planes of the last column —
 // and the ghost columns, which were wrapped by the first pass before they were sent.
-__global__ void k_wrap_y(double *f, Layout L, int wrap_to_bottom, int wrap_to_top, int after_exchange) {
+__global__ void k_wrap_y(double *f, PopShift ps, Layout L, int wrap_to_bottom, int wrap_to_top, int after_exchange) {
 	const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (c > L.nxl + 1) return;
-	wrap_y_column(f, L, wrap_to_bottom, wrap_to_top, after_exchange, c);
+	wrap_y_column(f, ps, L, wrap_to_bottom, wrap_to_top, after_exchange, c);
 }
 
 int launch_wrap_y(life_ctx *ctx, cudaStream_t st, bool after_exchange) {
 	const int wb = ctx->cfg.wall_bottom == LIFE_FLUID, wt = ctx->cfg.wall_top == LIFE_FLUID;
 	if (!wb && !wt) return LIFE_OK;
 	const int64_t n = ctx->L.nxl + 2;
-	k_wrap_y<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ctx->fB, ctx->L, wb, wt, after_exchange ? 1 : 0);
+	k_wrap_y<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ctx->inplace ? ctx->fA : ctx->fB, ctx->shift, ctx->L, wb, wt, after_exchange ? 1 : 0);
 	ctx->launches++;
 	LIFE_CUDA(ctx, cudaGetLastError());
 	return LIFE_OK;
@@ -102,8 +102,28 @@ namespace exact {
 #include "lbm_boundary.cuh"
 #endif   // LIFE_EXACT
 
-__global__ void __launch_bounds__(1024) k_convective_speed(const double *f, const double *stored, Layout L, ForceView fv, double *delU) {
-	convective_speed_block(f, stored, L, fv, delU);
+__global__ void __launch_bounds__(1024) k_convective_speed(const double *f, PopShift ps, const double *stored, Layout L, ForceView fv, double *delU) {
+	convective_speed_block(f, ps, stored, L, fv, delU);
+}
+
+// cfg.inplace: the sweep overwrites the state it reads, so what the boundary kernel needs of the state BEFORE the sweep is saved first,
+// 3 doubles per BCVec entry: f_n[2], f_n[6], f_n[8] of a convective outlet node (src/Grid.cpp:468-474), u_n of a pressure corner (the
+// normal component applyBCs leaves untouched, src/Grid.cpp:356-369).
+__global__ void __launch_bounds__(128) k_bc_capture(const BcNode *bc, int64_t n, const double *f, PopShift ps, Layout L, ForceView fprv, double *out) {
+	const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= n) return;
+	const BcNode bn = bc[b];
+	const int64_t idx = L.node(bn.il, bn.j);
+	if (bn.type == LIFE_CONVECTIVE) {
+		out[3 * b] = f[ps.at(2, idx, L.S)];
+		out[3 * b + 1] = f[ps.at(6, idx, L.S)];
+		out[3 * b + 2] = f[ps.at(8, idx, L.S)];
+	} else if (bn.type == LIFE_PRESSURE && bn.nx != 0 && bn.ny != 0) {
+		double r, ux, uy;
+		macro_end(f, ps, L, fprv, idx, r, ux, uy);
+		out[3 * b] = ux;
+		out[3 * b + 1] = uy;
+	}
 }
 
 template <int COLL>
@@ -123,8 +143,25 @@ int launch_convective_speed(life_ctx *ctx, const StepScalars &sc) {
 	if (ctx->cfg.wall_right != LIFE_CONVECTIVE || ctx->i_end != ctx->cfg.Nx) return LIFE_OK;
 	if (ctx->L.nxl < 3) return fail(ctx, LIFE_E_ARG, "convective outlet needs the last three columns on one rank");
 	ForceView fv = force_view(ctx, sc.fxy_prev);
-	k_convective_speed<<<1, 1024, 0, ctx->stream>>>(ctx->fA, ctx->stored_macro_valid ? ctx->macro : nullptr, ctx->L, fv,
+	k_convective_speed<<<1, 1024, 0, ctx->stream>>>(ctx->fA, ctx->shift, ctx->stored_macro_valid ? ctx->macro : nullptr, ctx->L, fv,
 	                                                ctx->delU);
+	ctx->launches++;
+	LIFE_CUDA(ctx, cudaGetLastError());
+	return LIFE_OK;
+}
+
+#ifdef LIFE_EXACT
+int launch_bc_capture_exact(life_ctx *ctx, const StepScalars &sc) {
+#else
+int launch_bc_capture(life_ctx *ctx, const StepScalars &sc) {
+#endif
+	if (!ctx->inplace || ctx->n_bc == 0) return LIFE_OK;
+	const bool needed = ctx->cfg.wall_right == LIFE_CONVECTIVE || ctx->cfg.wall_left == LIFE_PRESSURE || ctx->cfg.wall_right == LIFE_PRESSURE ||
+	                    ctx->cfg.wall_bottom == LIFE_PRESSURE || ctx->cfg.wall_top == LIFE_PRESSURE;
+	if (!needed) return LIFE_OK;
+	if (!ctx->bc_prev) LIFE_CUDA(ctx, cudaMalloc(&ctx->bc_prev, sizeof(double) * 3 * (size_t)ctx->n_bc));
+	k_bc_capture<<<(unsigned)((ctx->n_bc + 127) / 128), 128, 0, ctx->stream>>>(ctx->bc, ctx->n_bc, ctx->fA, ctx->shift, ctx->L,
+	                                                                          force_view(ctx, sc.fxy_prev), ctx->bc_prev);
 	ctx->launches++;
 	LIFE_CUDA(ctx, cudaGetLastError());
 	return LIFE_OK;

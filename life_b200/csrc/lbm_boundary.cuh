@@ -21,16 +21,16 @@ struct ForceView {
 	}
 };
 
-__device__ __forceinline__ void load9(const double *f, int64_t S, int64_t idx, double (&o)[NV]) {
+__device__ __forceinline__ void load9(const double *f, const PopShift &ps, int64_t S, int64_t idx, double (&o)[NV]) {
 #pragma unroll
-	for (int v = 0; v < NV; v++) o[v] = f[v * S + idx];
+	for (int v = 0; v < NV; v++) o[v] = f[ps.at(v, idx, S)];
 }
 
 // rho and u of GridClass::macroscopic (src/Grid.cpp:282-299): u = (sum c f + F_xy/2)/rho — no IBM force (mid-step value)
-__device__ __forceinline__ void macro_mid(const double *f, const Layout &L, const ForceView &fv, int64_t idx, double &rho,
+__device__ __forceinline__ void macro_mid(const double *f, const PopShift &ps, const Layout &L, const ForceView &fv, int64_t idx, double &rho,
                                           double &ux, double &uy) {
 	double p[NV], mx, my, fx, fy;
-	load9(f, L.S, idx, p);
+	load9(f, ps, L.S, idx, p);
 	moments(p, rho, mx, my);
 	fv.xy(idx, fx, fy);
 	ux = (mx + 0.5 * fx) / rho;
@@ -38,10 +38,10 @@ __device__ __forceinline__ void macro_mid(const double *f, const Layout &L, cons
 }
 
 // end-of-step value: u = (sum c f + (F_xy + F_ibm)/2)/rho (src/IBMNode.cpp:121-122; equals macroscopic() off-support)
-__device__ __forceinline__ void macro_end(const double *f, const Layout &L, const ForceView &fv, int64_t idx, double &rho,
+__device__ __forceinline__ void macro_end(const double *f, const PopShift &ps, const Layout &L, const ForceView &fv, int64_t idx, double &rho,
                                           double &ux, double &uy) {
 	double p[NV], mx, my, fx, fy, gx, gy;
-	load9(f, L.S, idx, p);
+	load9(f, ps, L.S, idx, p);
 	moments(p, rho, mx, my);
 	fv.xy(idx, fx, fy);
 	fv.ibm(idx, gx, gy);
@@ -55,7 +55,7 @@ __device__ __forceinline__ void macro_end(const double *f, const Layout &L, cons
 // uploaded macroscopics on the first step).  The column mean is a fixed-shape tree sum (deterministic).
 // ---------------------------------------------------------------------------------------------------------------------
 // block-level: call with ALL threads of one CTA (blockDim.x a power of two <= 1024)
-__device__ __forceinline__ void convective_speed_block(const double *f, const double *stored, const Layout &L, const ForceView &fv, double *delU) {
+__device__ __forceinline__ void convective_speed_block(const double *f, const PopShift &ps, const double *stored, const Layout &L, const ForceView &fv, double *delU) {
 	const int64_t c1 = L.nxl, c2 = L.nxl - 1, c3 = L.nxl - 2;   // local columns of i = Nx-1, Nx-2, Nx-3
 #ifdef LIFE_EXACT
 	// the reference's serial loop (src/Grid.cpp:483-487): every thread fetches its u_x, one thread adds them up in j order
@@ -64,7 +64,7 @@ __device__ __forceinline__ void convective_speed_block(const double *f, const do
 		const int64_t idx = L.at(c1, j + JOFF);
 		double rho, ux, uy;
 		if (stored) ux = stored[L.S + idx];
-		else macro_end(f, L, fv, idx, rho, ux, uy);
+		else macro_end(f, ps, L, fv, idx, rho, ux, uy);
 		delU[2 * j] = ux;                                   // staging: overwritten with delU below, after the sum has been read
 	}
 	__syncthreads();
@@ -82,7 +82,7 @@ __device__ __forceinline__ void convective_speed_block(const double *f, const do
 		const int64_t idx = L.at(c1, j + JOFF);
 		double rho, ux, uy;
 		if (stored) ux = stored[L.S + idx];
-		else macro_end(f, L, fv, idx, rho, ux, uy);
+		else macro_end(f, ps, L, fv, idx, rho, ux, uy);
 		part += ux;
 	}
 	red[threadIdx.x] = part;
@@ -101,9 +101,9 @@ __device__ __forceinline__ void convective_speed_block(const double *f, const do
 			b[0] = stored[L.S + i2]; b[1] = stored[2 * L.S + i2];
 			c[0] = stored[L.S + i3]; c[1] = stored[2 * L.S + i3];
 		} else {
-			macro_end(f, L, fv, i1, r, a[0], a[1]);
-			macro_end(f, L, fv, i2, r, b[0], b[1]);
-			macro_end(f, L, fv, i3, r, c[0], c[1]);
+			macro_end(f, ps, L, fv, i1, r, a[0], a[1]);
+			macro_end(f, ps, L, fv, i2, r, b[0], b[1]);
+			macro_end(f, ps, L, fv, i3, r, c[0], c[1]);
 		}
 		delU[2 * j] = (-uOut / 2.0) * (3.0 * a[0] - 4.0 * b[0] + c[0]);
 		delU[2 * j + 1] = (-uOut / 2.0) * (3.0 * a[1] - 4.0 * b[1] + c[1]);
@@ -126,8 +126,10 @@ static inline ForceView force_view(life_ctx *ctx, const double uni[2]) {
 struct BcArgs {
 	const BcNode *bc;
 	int64_t n;
-	const double *fprev;      // state before this step (f_n): convective outlet, stale u_n component
+	const double *fprev;      // state before this step (f_n): convective outlet, stale u_n component (null when `captured` is set)
 	double *f;                // freshly streamed populations (f)
+	PopShift ps;              // layout of f (and of fprev in the two-buffer mode, where it is all zero)
+	const double *captured;   // cfg.inplace: per BCVec entry, what is needed of the state before the sweep (k_bc_capture), else null
 	const double *stored;     // uploaded u_n/rho_n if this is the first step, else nullptr
 	Layout L;
 	ForceView fcur;           // forces of this step (new macroscopics of neighbours)
@@ -145,14 +147,17 @@ __device__ __forceinline__ void bc_node(const BcArgs &a, const int64_t b) {
 
 	if (type == LIFE_CONVECTIVE) {   // convectiveBC, src/Grid.cpp:468-474: only the three incoming populations
 		const double dux = a.delU[2 * bn.j], duy = a.delU[2 * bn.j + 1];
-		a.f[2 * L.S + idx] = a.fprev[2 * L.S + idx] + 3.0 * W1 * (dux * -1.0 + duy * 0.0);
-		a.f[6 * L.S + idx] = a.fprev[6 * L.S + idx] + 3.0 * W2 * (dux * -1.0 + duy * -1.0);
-		a.f[8 * L.S + idx] = a.fprev[8 * L.S + idx] + 3.0 * W2 * (dux * -1.0 + duy * 1.0);
+		const double p2 = a.captured ? a.captured[3 * b] : a.fprev[2 * L.S + idx];
+		const double p6 = a.captured ? a.captured[3 * b + 1] : a.fprev[6 * L.S + idx];
+		const double p8 = a.captured ? a.captured[3 * b + 2] : a.fprev[8 * L.S + idx];
+		a.f[a.ps.at(2, idx, L.S)] = p2 + 3.0 * W1 * (dux * -1.0 + duy * 0.0);
+		a.f[a.ps.at(6, idx, L.S)] = p6 + 3.0 * W2 * (dux * -1.0 + duy * -1.0);
+		a.f[a.ps.at(8, idx, L.S)] = p8 + 3.0 * W2 * (dux * -1.0 + duy * 1.0);
 		return;
 	}
 
 	double f[NV];
-	load9(a.f, L.S, idx, f);
+	load9(a.f, a.ps, L.S, idx, f);
 
 	// u_n / rho_n start as the end-of-previous-step values of this node (they are only read back in one case: the normal
 	// velocity of a pressure corner, which applyBCs leaves untouched)
@@ -160,7 +165,8 @@ __device__ __forceinline__ void bc_node(const BcArgs &a, const int64_t b) {
 	const bool corner = (nx != 0 && ny != 0);
 	if (type == LIFE_PRESSURE && corner) {
 		if (a.stored) { un[0] = a.stored[L.S + idx]; un[1] = a.stored[2 * L.S + idx]; }
-		else { double r; macro_end(a.fprev, L, a.fprv, idx, r, un[0], un[1]); }
+		else if (a.captured) { un[0] = a.captured[3 * b]; un[1] = a.captured[3 * b + 1]; }
+		else { double r; macro_end(a.fprev, a.ps, L, a.fprv, idx, r, un[0], un[1]); }
 	}
 
 	// interior neighbours along the normal (inc/Utils.h:151-161, :200-210)
@@ -174,8 +180,8 @@ __device__ __forceinline__ void bc_node(const BcArgs &a, const int64_t b) {
 		un[1] = a.u_in[2 * bn.j + 1] * a.ramp;
 	} else {   // free slip / pressure: tangential velocity by 2nd-order zero gradient of the NEW u
 		double r1, u1[2], r2, u2[2];
-		macro_mid(a.f, L, a.fcur, i1, r1, u1[0], u1[1]);
-		macro_mid(a.f, L, a.fcur, i2, r2, u2[0], u2[1]);
+		macro_mid(a.f, a.ps, L, a.fcur, i1, r1, u1[0], u1[1]);
+		macro_mid(a.f, a.ps, L, a.fcur, i2, r2, u2[0], u2[1]);
 		const int dt = 1 - nd;
 		if (type == LIFE_FREESLIP) un[nd] = 0.0;
 		else rhon = a.rho_in[bn.j];
@@ -187,8 +193,8 @@ __device__ __forceinline__ void bc_node(const BcArgs &a, const int64_t b) {
 	if (corner) {
 		if (type != LIFE_PRESSURE) {   // density extrapolated along the diagonal from the NEW rho (src/Grid.cpp:394)
 			double r1, r2, t0, t1;
-			macro_mid(a.f, L, a.fcur, i1, r1, t0, t1);
-			macro_mid(a.f, L, a.fcur, i2, r2, t0, t1);
+			macro_mid(a.f, a.ps, L, a.fcur, i1, r1, t0, t1);
+			macro_mid(a.f, a.ps, L, a.fcur, i2, r2, t0, t1);
 			rhon = 2.0 * r1 - r2;
 		}
 	} else {
@@ -230,7 +236,7 @@ __device__ __forceinline__ void bc_node(const BcArgs &a, const int64_t b) {
 	for (int v = 0; v < NV; v++) {
 		const int cx = kCx[v], cy = kCy[v];
 		const double w = v == 0 ? W0 : (v < 5 ? W1 : W2);
-		a.f[v * L.S + idx] = feq[v] + (w / (2.0 * CS4)) * (((cx * cx - CS2) * Sxx) + ((cy * cy - CS2) * Syy) + (2.0 * cx * cy * Sxy));
+		a.f[a.ps.at(v, idx, L.S)] = feq[v] + (w / (2.0 * CS4)) * (((cx * cx - CS2) * Sxx) + ((cy * cy - CS2) * Syy) + (2.0 * cx * cy * Sxy));
 	}
 }
 
@@ -238,6 +244,11 @@ static inline BcArgs make_bc_args(life_ctx *ctx, const StepScalars &sc) {
 	BcArgs a{};
 	a.bc = ctx->bc; a.n = ctx->n_bc;
 	a.fprev = ctx->fA; a.f = ctx->fB;
+	if (ctx->inplace) {      // one buffer, already advanced to the post-stream layout; the pre-sweep values come from k_bc_capture
+		a.fprev = nullptr; a.f = ctx->fA;
+		a.ps = ctx->shift;
+		a.captured = ctx->bc_prev;
+	}
 	a.stored = ctx->stored_macro_valid ? ctx->macro : nullptr;
 	a.L = ctx->L;
 	a.fcur = force_view(ctx, sc.fxy_cur);
@@ -248,19 +259,19 @@ static inline BcArgs make_bc_args(life_ctx *ctx, const StepScalars &sc) {
 }
 
 // y wrap-around of one column c of the ghost ring (see lbm_boundary.cu: k_wrap_y)
-__device__ __forceinline__ void wrap_y_column(double *f, const Layout &L, int wrap_to_bottom, int wrap_to_top, int after_exchange, int64_t c) {
+__device__ __forceinline__ void wrap_y_column(double *f, const PopShift &ps, const Layout &L, int wrap_to_bottom, int wrap_to_top, int after_exchange, int64_t c) {
 	if (after_exchange && (c == 0 || c == L.nxl + 1)) return;
 	const bool skip_plus = after_exchange && c == 1;        // cx = +1 planes: 5 (cy=+1), 7 (cy=-1)
 	const bool skip_minus = after_exchange && c == L.nxl;   // cx = -1 planes: 8 (cy=+1), 6 (cy=-1)
 	const int64_t base = c * L.P;
 	if (wrap_to_bottom) {   // cy = +1 populations: v = 3, 5, 8
-		f[3 * L.S + base + JOFF] = f[3 * L.S + base + JOFF + L.Ny];
-		if (!skip_plus) f[5 * L.S + base + JOFF] = f[5 * L.S + base + JOFF + L.Ny];
-		if (!skip_minus) f[8 * L.S + base + JOFF] = f[8 * L.S + base + JOFF + L.Ny];
+		f[ps.at(3, base + JOFF, L.S)] = f[ps.at(3, base + JOFF + L.Ny, L.S)];
+		if (!skip_plus) f[ps.at(5, base + JOFF, L.S)] = f[ps.at(5, base + JOFF + L.Ny, L.S)];
+		if (!skip_minus) f[ps.at(8, base + JOFF, L.S)] = f[ps.at(8, base + JOFF + L.Ny, L.S)];
 	}
 	if (wrap_to_top) {      // cy = -1 populations: v = 4, 6, 7
-		f[4 * L.S + base + JOFF + L.Ny - 1] = f[4 * L.S + base + JOFF - 1];
-		if (!skip_minus) f[6 * L.S + base + JOFF + L.Ny - 1] = f[6 * L.S + base + JOFF - 1];
-		if (!skip_plus) f[7 * L.S + base + JOFF + L.Ny - 1] = f[7 * L.S + base + JOFF - 1];
+		f[ps.at(4, base + JOFF + L.Ny - 1, L.S)] = f[ps.at(4, base + JOFF - 1, L.S)];
+		if (!skip_minus) f[ps.at(6, base + JOFF + L.Ny - 1, L.S)] = f[ps.at(6, base + JOFF - 1, L.S)];
+		if (!skip_plus) f[ps.at(7, base + JOFF + L.Ny - 1, L.S)] = f[ps.at(7, base + JOFF - 1, L.S)];
 	}
 }

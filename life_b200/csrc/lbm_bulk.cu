@@ -46,6 +46,31 @@ __global__ void __launch_bounds__(256) k_bulk_direct(const BulkArgs a) {
 	for (int v = 0; v < NV; v++) a.fout[v * a.L.S + idx + LIFE_CX(v) * a.L.P + LIFE_CY(v)] = o[v];
 }
 
+// ---- SHIFT: the in-place sweep (cfg.inplace), ONE population buffer -----------------------------------------------------------------------
+// Population v of logical element n sits at plane element (n - off_v) mod S (ctx.h: PopShift).  A node reads its nine populations,
+// collides, and writes every result back to the slot it was read from: with off_v growing by shift_v = cx*P + cy after the sweep,
+// that slot IS element n + shift_v of the next step's layout — the push to the neighbour happens by renaming, not by moving data.
+// No second buffer, no ordering constraint between nodes (each touches only its own nine slots), the same kernel every step, and
+// the same 144 B/node of traffic.  The offsets change parity every step, so accesses are 8-byte (fully coalesced along y; the DIRECT
+// variant shows what that costs against 16-byte accesses: ~1 %).
+template <int COLL, int MODE>
+__global__ void __launch_bounds__(256) k_bulk_shift(const BulkArgs a) {
+	const int64_t col = a.c_first + blockIdx.x / a.tiles;
+	const int64_t j = (int64_t)(blockIdx.x % a.tiles) * blockDim.x + threadIdx.x;
+	if (j >= a.L.Ny) return;
+	const int64_t idx = col * a.L.P + j + JOFF;
+	int64_t at[NV];
+	double f[NV], o[NV];
+#pragma unroll
+	for (int v = 0; v < NV; v++) {
+		at[v] = a.ps.at(v, idx, a.L.S);
+		f[v] = a.fout[at[v]];
+	}
+	node_update<COLL, MODE>(a, idx, f, o, ibm_span(a, col, j));
+#pragma unroll
+	for (int v = 0; v < NV; v++) a.fout[at[v]] = o[v];
+}
+
 // ---- SHUFFLE: two nodes per thread, warp-shuffle realignment of the y-moving populations -------------------------------------
 // A warp owns 64 consecutive rows R..R+63 (R even) of one column.  Thread `lane` holds rows R+2*lane and R+2*lane+1.
 // Population with cy = +1: row q goes to row q+1.  The aligned pair (R+2l, R+2l+1) of the destination therefore consists of
@@ -308,9 +333,19 @@ static int launch_tma(life_ctx *ctx, BulkArgs a, int64_t c_count, cudaStream_t s
 template <int COLL, int MODE>
 static int launch_one(life_ctx *ctx, const BulkArgs &a0, int64_t c_count, cudaStream_t st) {
 #ifndef LIFE_EXACT
-	if (ctx->cfg.kernel == LIFE_KERNEL_TMA) return launch_tma<COLL, MODE>(ctx, a0, c_count, st);
+	if (ctx->cfg.kernel == LIFE_KERNEL_TMA && !ctx->inplace) return launch_tma<COLL, MODE>(ctx, a0, c_count, st);
 #endif
 	BulkArgs a = a0;
+	if (ctx->inplace) {
+		a.tiles = (a.L.Ny + 255) / 256;
+		const int64_t blocks = a.tiles * c_count;
+		if (blocks <= 0) return LIFE_OK;
+		if (blocks > 0x7fffffffLL) return fail(ctx, LIFE_E_ARG, "bulk sweep: grid too large");
+		k_bulk_shift<COLL, MODE><<<(unsigned)blocks, 256, 0, st>>>(a);
+		ctx->launches++;
+		LIFE_CUDA(ctx, cudaGetLastError());
+		return LIFE_OK;
+	}
 	if (ctx->cfg.kernel == LIFE_KERNEL_QUAD && a.L.Ny % 128 == 0) {
 		const int block = ctx->cfg.tune == 1 ? 128 : 256;
 		a.tiles = (a.L.Ny + 4 * block - 1) / (4 * block);

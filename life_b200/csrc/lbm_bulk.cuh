@@ -6,6 +6,7 @@
 struct BulkArgs {
 	const double *fin;
 	double *fout;
+	PopShift ps;            // cfg.inplace: layout of the ONE buffer (fin == fout); all zero otherwise
 	Layout L;
 	double omega;
 	double fup_x, fup_y;    // uniform force_xy entering u_n   (previous step's value)
@@ -96,7 +97,8 @@ __device__ __forceinline__ void node_update(const BulkArgs &a, int64_t idx, cons
 static inline BulkArgs make_bulk_args(life_ctx *ctx, const StepScalars &sc, int64_t c_first, int *mode_out) {
 	BulkArgs a{};
 	a.fin = ctx->fA;
-	a.fout = ctx->fB;
+	a.fout = ctx->inplace ? ctx->fA : ctx->fB;
+	a.ps = ctx->shift;
 	a.L = ctx->L;
 	a.omega = ctx->cfg.omega;
 	a.fup_x = sc.fxy_prev[0]; a.fup_y = sc.fxy_prev[1];

@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(256) k_restart_pack(const MacroArgs a, const d
 		double p[NV], rho, ux, uy;
 		if (stored) {
 #pragma unroll
-			for (int v = 0; v < NV; v++) p[v] = __ldg(a.f + v * a.L.S + idx);
+			for (int v = 0; v < NV; v++) p[v] = __ldg(a.f + a.ps.at(v, idx, a.L.S));
 			rho = stored[idx]; ux = stored[a.L.S + idx]; uy = stored[2 * a.L.S + idx];
 		} else {
 			node_macro_p(a, idx, p, rho, ux, uy);

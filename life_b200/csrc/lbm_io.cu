@@ -50,13 +50,13 @@ __global__ void k_unpack(const double *__restrict__ src, double *__restrict__ pl
 }
 
 __global__ void k_pack(double *__restrict__ dst, const double *__restrict__ planes, Layout L, int ncomp, int64_t il0,
-                       int64_t n_elems) {
+                       int64_t n_elems, PopShift ps) {
 	const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (e >= n_elems) return;
 	const int64_t node = e / ncomp;
 	const int k = (int)(e - node * ncomp);
 	const int64_t il = il0 + node / L.Ny, j = node % L.Ny;
-	dst[e] = planes[k * L.S + L.node(il, j)];
+	dst[e] = planes[ps.at(k, L.node(il, j), L.S)];     // ps: zeros for everything but in-place populations
 }
 
 static int64_t chunk_columns(life_ctx *ctx, int ncomp) {
@@ -86,15 +86,16 @@ int upload_field(life_ctx *ctx, const double *h, double *planes, int ncomp, int6
 	return LIFE_OK;
 }
 
-int download_field(life_ctx *ctx, double *h, const double *planes, int ncomp, int64_t il0, int64_t ncols) {
+int download_field(life_ctx *ctx, double *h, const double *planes, int ncomp, int64_t il0, int64_t ncols, const PopShift *ps) {
 	const Layout &L = ctx->L;
+	const PopShift shift = ps ? *ps : PopShift{};
 	const int64_t cols = chunk_columns(ctx, ncomp);
 	int rc = ensure_scratch(ctx, sizeof(double) * (size_t)(cols * L.Ny * ncomp));
 	if (rc) return rc;
 	for (int64_t c0 = 0; c0 < ncols; c0 += cols) {
 		const int64_t nc = (c0 + cols <= ncols) ? cols : ncols - c0;
 		const int64_t n_elems = nc * L.Ny * ncomp;
-		k_pack<<<(unsigned)((n_elems + 255) / 256), 256, 0, ctx->stream>>>(ctx->scratch, planes, L, ncomp, il0 + c0, n_elems);
+		k_pack<<<(unsigned)((n_elems + 255) / 256), 256, 0, ctx->stream>>>(ctx->scratch, planes, L, ncomp, il0 + c0, n_elems, shift);
 		ctx->launches++;
 		LIFE_CUDA(ctx, cudaGetLastError());
 		LIFE_CUDA(ctx, cudaMemcpyAsync(h + c0 * L.Ny * ncomp, ctx->scratch, sizeof(double) * n_elems,
@@ -139,6 +140,9 @@ __global__ void __launch_bounds__(256) k_macro(const MacroArgs a, double *out, i
 MacroArgs macro_args(life_ctx *ctx) {
 	MacroArgs a{};
 	a.f = ctx->fA;
+	a.ps = ctx->shift;
+	a.shifted = 0;
+	for (int v = 0; v < 9; v++) a.shifted |= ctx->shift.off[v] != 0;
 	a.L = ctx->L;
 	a.fxy_mode = ctx->fxy_mode;
 	a.fx = ctx->fxy_uniform[0]; a.fy = ctx->fxy_uniform[1];
@@ -179,7 +183,7 @@ __global__ void __launch_bounds__(256) k_max_speed(const MacroArgs a, const doub
 		if (stored) {
 			ux[0] = stored[a.L.S + idx]; uy[0] = stored[2 * a.L.S + idx];
 			ux[1] = two ? stored[a.L.S + idx + 1] : 0.0; uy[1] = two ? stored[2 * a.L.S + idx + 1] : 0.0;
-		} else if (a.fxy_mode == FXY_FIELD || a.fibm) {
+		} else if (a.fxy_mode == FXY_FIELD || a.fibm || a.shifted) {
 			double rho;
 			node_macro(a, idx, rho, ux[0], uy[0]);
 			if (two) node_macro(a, idx + 1, rho, ux[1], uy[1]);

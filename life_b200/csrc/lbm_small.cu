@@ -62,7 +62,7 @@ __global__ void __cluster_dims__(SMALL_CLUSTER, 1, 1) __launch_bounds__(SMALL_TH
 		c.fprv.ux = sc.fxy_prev[0]; c.fprv.uy = sc.fxy_prev[1];
 
 		// convective outlet speed from the state before the step (src/Grid.cpp:39-40): one CTA, finished before the boundary phase
-		if (a.convective && blockIdx.x == SMALL_CLUSTER - 1) convective_speed_block(fin, nullptr, L, c.fprv, const_cast<double *>(c.delU));
+		if (a.convective && blockIdx.x == SMALL_CLUSTER - 1) convective_speed_block(fin, PopShift{}, nullptr, L, c.fprv, const_cast<double *>(c.delU));
 
 		// sweep: stream + collide of every node (src/Grid.cpp:65-84)
 		for (int64_t n = tid; n < nodes; n += nth) {
@@ -80,7 +80,7 @@ __global__ void __cluster_dims__(SMALL_CLUSTER, 1, 1) __launch_bounds__(SMALL_TH
 		// ghost ring: periodic wrap in y, then in x (the modulo of src/Grid.cpp:229); the x copies read what the y wrap wrote in the
 		// ghost columns, hence the second barrier — only taken by lattices that are periodic somewhere
 		if (a.wrap_bottom || a.wrap_top) {
-			for (int64_t col = tid; col <= L.nxl + 1; col += nth) wrap_y_column(fout, L, a.wrap_bottom, a.wrap_top, 0, col);
+			for (int64_t col = tid; col <= L.nxl + 1; col += nth) wrap_y_column(fout, PopShift{}, L, a.wrap_bottom, a.wrap_top, 0, col);
 			cluster.sync();
 		}
 		if (a.left_periodic || a.right_periodic) {

@@ -8,6 +8,8 @@ namespace life {
 
 struct MacroArgs {
 	const double *f;
+	PopShift ps;          // layout of f (zeros unless cfg.inplace)
+	int shifted;          // any offset non-zero
 	Layout L;
 	int fxy_mode;
 	double fx, fy;
@@ -19,7 +21,7 @@ struct MacroArgs {
 __device__ __forceinline__ void node_macro_p(const MacroArgs &a, int64_t idx, double (&p)[NV], double &rho, double &ux, double &uy) {
 	double mx, my;
 #pragma unroll
-	for (int v = 0; v < NV; v++) p[v] = __ldg(a.f + v * a.L.S + idx);
+	for (int v = 0; v < NV; v++) p[v] = __ldg(a.f + a.ps.at(v, idx, a.L.S));
 	moments(p, rho, mx, my);
 	double fx = a.fx, fy = a.fy;
 	if (a.fxy_mode == FXY_FIELD) { fx = a.fxyf[idx]; fy = a.fxyf[a.L.S + idx]; }

@@ -34,7 +34,8 @@ def main():
     g = K.golden(case)
     steps = (int(sys.argv[2]) if len(sys.argv) > 2 else 0) or int(g["steps"])
     o = K.make_oracle(g)
-    cfg = K.life_config(o.params, o, rank=rank, nranks=world, device=local)
+    extra = dict(inplace=1) if os.environ.get("LIFE_TEST_INPLACE") == "1" else {}     # cfg.inplace: one population buffer, shifted layout
+    cfg = K.life_config(o.params, o, rank=rank, nranks=world, device=local, **extra)
     ctx = capi.Context(cfg, nccl_id=nid)
     Nx = o.Nx
     b, e = ctx.i_begin, ctx.i_end
@@ -95,7 +96,7 @@ def main():
                     ok = False
                     msgs.append("shared Fluid.restart differs (mode %d)" % mode)
             dist.barrier()
-        back = capi.Context(K.life_config(o.params, o, rank=rank, nranks=world, device=local), nccl_id=D.share_nccl_id())
+        back = capi.Context(K.life_config(o.params, o, rank=rank, nranks=world, device=local, **extra), nccl_id=D.share_nccl_id())
         t_file = back.read_restart(rst, o.get("force_xy").reshape(-1, 2)[0], o.get("u_in"), o.get("rho_in"))
         sb = back.download_state()
         back.close()

@@ -27,14 +27,15 @@ def _port():
     return p
 
 
-def _launch(n, case, steps=None, outdir=None):
+def _launch(n, case, steps=None, outdir=None, inplace=False):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr",
            "127.0.0.1", "--master-port", str(_port()), os.path.join(ROOT, "tests", "mp_parity.py"), case]
     if steps or outdir:
         cmd.append(str(steps or 0))
     if outdir:
         cmd.append(str(outdir))
-    return subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    env = dict(os.environ, LIFE_TEST_INPLACE="1" if inplace else "0")
+    return subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
 
 
 # walls + corners, pressure/velocity ends, periodic x ring, y-periodic wrap at the faces, free slip, convective outlet
@@ -73,3 +74,14 @@ def test_slabs_write_one_file_together(case, n, tmp_path):
     p = _launch(n, case, outdir=tmp_path)
     assert p.returncode == 0, p.stdout[-3000:]
     assert p.stdout.count(": ok") == n, p.stdout[-3000:]
+
+
+@pytest.mark.parametrize("case", ["ChannelFlow", "t_periodic_cm", "t_yperiodic", "t_convective", "t_womersley", "Honami", "PELskin"])
+def test_two_slabs_match_with_the_inplace_layout(case, tmp_path):
+    """cfg.inplace across slabs: the halo travels through contiguous staging buffers (the planes are circular), the shared files are
+    written from the shifted layout."""
+    if _ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    p = _launch(2, case, outdir=str(tmp_path) if case in ("ChannelFlow", "t_periodic_cm") else None, inplace=True)
+    assert p.returncode == 0, p.stdout[-3000:]
+    assert p.stdout.count(": ok") == 2, p.stdout[-3000:]

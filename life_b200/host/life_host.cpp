@@ -154,6 +154,9 @@ life_config make_config(const GridClass &g) {
 	// LIFE_B200_EXACT=1: the step in the reference's operation order (bitwise equal Results/, the reference's own `diff -r` protocol)
 	const char *x = std::getenv("LIFE_B200_EXACT");
 	c.exact = x ? std::atoi(x) : 0;
+	// LIFE_B200_INPLACE=1: one population buffer (72 B/node resident), in-place sweep
+	const char *ip = std::getenv("LIFE_B200_INPLACE");
+	c.inplace = ip ? std::atoi(ip) : 0;
 	return c;
 }
 

@@ -17,6 +17,7 @@
 //     ref_P [0] ref_L [height_p] ref_nu [nu_p]     reference values of the printed report / the pressure block
 //     gpus [1]                       x-slabs = GPUs = host threads
 //     exact [0]                      cfg.exact: the reference's operation order, bitwise its results
+//     inplace [0]                    cfg.inplace: one population buffer (72 B/node resident)
 //     results [Results]              output directory (VTK/ and Restart/ below it, as the reference lays them out)
 //
 // What it does is src/main.cpp:25-94 + GridClass::GridClass / initialiseGrid (src/Grid.cpp:916-1062, :1232-1289) restated for
@@ -161,6 +162,7 @@ int main(int argc, char **argv) {
 	cfg.device = -1; cfg.nranks = 1;
 	cfg.exact = c.num("exact", 0) != 0;
 	cfg.kernel = (int)c.num("kernel", 0);
+	cfg.inplace = c.num("inplace", 0) != 0;
 	unsigned char nccl_id[128] = {0};
 	if (gpus > 1 && life_nccl_unique_id(nccl_id) != LIFE_OK) fatal(std::string("life_nccl_unique_id: ") + life_last_error(nullptr));
 	std::vector<life_ctx *> ctx((size_t)gpus, nullptr);

@@ -162,7 +162,7 @@ def _diff_r(ref_dir, new_dir):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("variant", ["default", "host-eps", "host-io"])
+@pytest.mark.parametrize("variant", ["default", "host-eps", "host-io", "inplace"])
 @pytest.mark.parametrize("case", [c for c in EXAMPLES if c != "LidDrivenCavity"])
 def test_program_in_exact_mode_is_bitwise_the_reference(case, variant, tmp_path):
     """The reference's own regression protocol, unrelaxed: LIFE_b200 with LIFE_B200_EXACT=1 (cfg.exact: the step in the
@@ -172,7 +172,7 @@ def test_program_in_exact_mode_is_bitwise_the_reference(case, variant, tmp_path)
     (TurekHron, InvertedFlag, Honami, PELskin).  All six cases are BGK (LidDrivenCavity is central moments, tested at 1e-10)."""
     if not (_have(case, "LIFE_b200") and _have(case, "LIFE_ref")):
         pytest.skip("life_b200/host/_build/%s not built (make -C life_b200/host needs /root/reference)" % case)
-    if variant != "default" and case not in ("ChannelFlow", "TurekHron", "PELskin"):
+    if variant not in ("default", "inplace") and case not in ("ChannelFlow", "TurekHron", "PELskin"):
         pytest.skip("the epsilon / host-mirror variants are exercised on one plain case and the two UNI_EPSILON restart / Womersley cases")
     times = 2 if case == "TurekHron" else 1
     ref = _run(case, "LIFE_ref", str(tmp_path / "ref"), times)
@@ -180,7 +180,8 @@ def test_program_in_exact_mode_is_bitwise_the_reference(case, variant, tmp_path)
     # default = epsilon matrix assembled on the device + the host's LAPACK, device-fed files; host-eps = the reference's own
     # computeEpsilon; host-io = downloads into the host mirrors + the reference's own writers / reader
     new = _run(case, "LIFE_b200", str(tmp_path / "b200"), times, LIFE_B200_EXACT="1",
-               LIFE_B200_DEVICE_EPSILON="0" if variant == "host-eps" else "1", LIFE_B200_HOST_IO="1" if variant == "host-io" else "0")
+               LIFE_B200_DEVICE_EPSILON="0" if variant == "host-eps" else "1", LIFE_B200_HOST_IO="1" if variant == "host-io" else "0",
+               LIFE_B200_INPLACE="1" if variant == "inplace" else "0")      # inplace: one population buffer, shifted layout (cfg.inplace)
     assert new.returncode == 0, new.stdout[-2000:] + new.stderr[-2000:]
     assert "life_step" in new.stderr and " 0 life_step" not in new.stderr      # the CUDA path really ran
     differing, n_files = _diff_r(str(tmp_path / "ref"), str(tmp_path / "b200"))

@@ -148,7 +148,8 @@ def test_persistent_small_lattice_kernel_is_bitwise_the_per_step_path(case, exac
             assert K.rel_l2(sb[name], sa[name], floor=1e-3 if name == "u" else 0.0) < 1e-13, (case, name)
     # first step (stored macroscopics of the upload) through the per-step path, the other N-1 in one launch
     per_step = (a.launch_count()) // N
-    assert launches <= per_step + 3, (launches, per_step)
+    if o.Nx * o.Ny <= 16384 and not (float(g["womersley"]) > 0 and (float(g["gravityX"]) != 0 or float(g["gravityY"]) != 0)):
+        assert launches <= per_step + 3, (launches, per_step)      # (larger lattices and force FIELDS keep the per-step kernels, csrc/api.cu)
     # and it continues correctly: more steps in a second batch, odd count (buffer parity)
     for t in range(N + 1, N + 8):
         a.step(t)

@@ -512,7 +512,7 @@ def run_gpu_arm(args):
     traffic, traffic_src = None, "none for this configuration"
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        key = "%s_%d" % (args.collision, S)
+        key = "%s_%d%s" % (args.collision, S, "_inplace" if args.inplace else "")
         if key in tr and world == 1:
             traffic = tr[key]["dram_bytes_per_launch"]
             traffic_src = "static: ncu --set full capture of this kernel on this workload, %s (profiles/traffic.json); not measured in this run" % tr[key].get("source", "profiles/")

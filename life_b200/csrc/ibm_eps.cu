@@ -14,6 +14,7 @@
 // UNI_EPSILON (one body holding every marker: TurekHron 132, PELskin 310) it is the largest host cost once the LBM step is on
 // the GPU.
 #include "ctx.h"
+#include <cooperative_groups.h>
 #include <cstring>
 
 namespace life {
@@ -175,6 +176,139 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_eps_solve(const EpsArgs a) {
 	for (int r = tid; r < dim; r += T) a.eps[a.members[m0 + r]] = x[r];
 }
 
+
+// ---- the same solve for LARGE systems (UNI_EPSILON: TurekHron 132, PELskin 310 markers) on one thread-block CLUSTER ---------------------
+// The single-CTA kernel above walks an L2-resident matrix and pays a global-memory round trip per elimination step (8 ms at dim =
+// 310; LAPACK on the host: 1.2 ms).  Here the matrix lives in the DISTRIBUTED SHARED MEMORY of a cluster of 8 CTAs: CTA q holds
+// the columns c = q, q+8, ... of M = A^T (cyclic, so the shrinking trailing matrix stays balanced), 96 KB each at dim = 310.  Per
+// elimination step the owner of column k finds the pivot (idamax rule), scales the column and writes the multipliers and the pivot
+// row into a broadcast buffer of EVERY CTA with remote shared-memory stores; one cluster barrier later all CTAs swap rows k / p and
+// update their own columns out of their own shared memory.  The buffers alternate, so a step costs one cluster barrier and no
+// global-memory access at all.  The two triangular solves of dgetrs('T') are done by CTA 0, which reads the columns it needs from its
+// peers' shared memory.  Same pivots as the kernel above and as LAPACK; sums are ordered differently from a blocked LAPACK, so epsilon
+// agrees to rounding x cond(A).
+constexpr int EC_CLUSTER = 8;
+constexpr int EC_THREADS = 512;
+
+__global__ void __cluster_dims__(EC_CLUSTER, 1, 1) __launch_bounds__(EC_THREADS, 1) k_eps_solve_cluster(const EpsArgs a) {
+	namespace cg = cooperative_groups;
+	cg::cluster_group cluster = cg::this_cluster();
+	extern __shared__ double ec_sm[];
+	__shared__ double sh[33];
+	__shared__ double s_best[EC_THREADS / 32];
+	__shared__ int s_idx[EC_THREADS / 32];
+	__shared__ int s_piv[512];
+	const int q = (int)cluster.block_rank();
+	const int b = blockIdx.x / EC_CLUSTER;
+	const int64_t m0 = a.first[b];
+	const int dim = (int)(a.first[b + 1] - m0);
+	const int tid = threadIdx.x, T = EC_THREADS;
+	const int ncl_max = (dim + EC_CLUSTER - 1) / EC_CLUSTER;
+	double *col = ec_sm;                                   // local column lc (global column q + 8 lc) at col + lc*dim
+	double *bc0 = col + (size_t)ncl_max * dim;             // broadcast buffers: [dim] multipliers, [dim] = pivot row, [dim+1] = zero-pivot flag
+	double *bc1 = bc0 + dim + 2;
+	double *y = bc1 + dim + 2, *z = y + dim;
+	const int ncl = dim > q ? (dim - q + EC_CLUSTER - 1) / EC_CLUSTER : 0;
+	const double *M = a.A + a.mat_off[b];                  // a.A[c*dim + r] = M(r, c), M = A^T column-major (see k_eps_solve)
+	for (int64_t e = tid; e < (int64_t)ncl * dim; e += T) {
+		const int lc = (int)(e / dim), r = (int)(e - (int64_t)lc * dim);
+		col[e] = M[(int64_t)(q + EC_CLUSTER * lc) * dim + r];
+	}
+	cluster.sync();
+
+	for (int k = 0; k < dim; k++) {
+		double *buf = (k & 1) ? bc1 : bc0;
+		if (q == k % EC_CLUSTER) {
+			double *ck = col + (size_t)(k / EC_CLUSTER) * dim;
+			double best = -1.0;
+			int bi = k;
+			for (int r = k + tid; r < dim; r += T) {
+				const double v = fabs(ck[r]);
+				if (v > best) { best = v; bi = r; }
+			}
+			for (int o = 16; o > 0; o >>= 1) {
+				const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+				const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+				if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+			}
+			if ((tid & 31) == 0) { s_best[tid >> 5] = best; s_idx[tid >> 5] = bi; }
+			__syncthreads();
+			if (tid == 0) {
+				double bb = s_best[0];
+				int ii = s_idx[0];
+				for (int w = 1; w < (T >> 5); w++)
+					if (s_best[w] > bb || (s_best[w] == bb && s_idx[w] < ii)) { bb = s_best[w]; ii = s_idx[w]; }
+				const double t = ck[k]; ck[k] = ck[ii]; ck[ii] = t;      // row interchange inside column k
+				s_idx[0] = ii;
+				s_best[0] = ck[k];
+				if (bb == 0.0) atomicExch(a.info, k + 1);
+			}
+			__syncthreads();
+			const int p = s_idx[0];
+			const double pv = s_best[0];
+			const double rp = pv != 0.0 ? 1.0 / pv : 1.0;              // dgetf2 scales by the reciprocal
+			for (int r = k + 1 + tid; r < dim; r += T) ck[r] *= rp;
+			__syncthreads();
+			// multipliers and pivot row into every CTA's buffer (remote shared-memory stores)
+			for (int d = 0; d < EC_CLUSTER; d++) {
+				double *dst = cluster.map_shared_rank(buf, d);
+				for (int r = k + 1 + tid; r < dim; r += T) dst[r] = ck[r];
+				if (tid == 0) dst[dim] = (double)p;
+			}
+		}
+		cluster.sync();
+		const int p = (int)buf[dim];
+		if (tid == 0) s_piv[k & 511] = p;
+		// dlaswp over the local columns (column k itself was interchanged by its owner), then the rank-1 update of the columns c > k
+		if (p != k)
+			for (int lc = tid; lc < ncl; lc += T) {
+				if (q + EC_CLUSTER * lc == k) continue;
+				double *c = col + (size_t)lc * dim;
+				const double t = c[k]; c[k] = c[p]; c[p] = t;
+			}
+		__syncthreads();
+		const int lc0 = k >= q ? (k - q) / EC_CLUSTER + 1 : 0;       // first local column with global index > k
+		const int m = dim - k - 1;
+		for (int64_t e = tid; e < (int64_t)(ncl - lc0) * m; e += T) {
+			const int lc = lc0 + (int)(e / m), r = k + 1 + (int)(e % m);
+			double *c = col + (size_t)lc * dim;
+			c[r] -= buf[r] * c[k];
+		}
+		__syncthreads();
+	}
+	cluster.sync();      // every column is final
+
+	// dgetrs('T') by CTA 0: U^T y = 1, L^T z = y, x = P^T z; column r of M sits in CTA r % 8 at local column r / 8
+	if (q == 0) {
+		for (int r = 0; r < dim; r++) {
+			const double *cr = cluster.map_shared_rank(col, r % EC_CLUSTER) + (size_t)(r / EC_CLUSTER) * dim;
+			double part = 0.0;
+			for (int c = tid; c < r; c += T) part += cr[c] * y[c];
+			const double s = block_sum(part, sh);
+			if (tid == 0) y[r] = (1.0 - s) / cr[r];
+			__syncthreads();
+		}
+		for (int r = tid; r < dim; r += T) z[r] = y[r];
+		__syncthreads();
+		for (int r = dim - 2; r >= 0; r--) {
+			const double *cr = cluster.map_shared_rank(col, r % EC_CLUSTER) + (size_t)(r / EC_CLUSTER) * dim;
+			double part = 0.0;
+			for (int c = r + 1 + tid; c < dim; c += T) part += cr[c] * z[c];
+			const double s = block_sum(part, sh);
+			if (tid == 0) z[r] -= s;
+			__syncthreads();
+		}
+		if (tid == 0)
+			for (int k = dim - 1; k >= 0; k--) {
+				const int p = s_piv[k];
+				if (p != k) { const double t = z[k]; z[k] = z[p]; z[p] = t; }
+			}
+		__syncthreads();
+		for (int r = tid; r < dim; r += T) a.eps[a.members[m0 + r]] = z[r];
+	}
+	cluster.sync();      // nobody leaves while CTA 0 still reads its shared memory
+}
+
 // uploads the group description, assembles every group's matrix; *out describes the device buffers
 static int eps_prepare(life_ctx *ctx, int64_t nb, const int64_t *first, const int64_t *members, const char *who, EpsArgs *out,
                        int64_t *a_elems_out) {
@@ -251,7 +385,17 @@ int ibm_compute_epsilon(life_ctx *ctx, int64_t nb, const int64_t *first, const i
 	int rc = eps_prepare(ctx, nb, first, members, "life_ibm_compute_epsilon", &a, &a_elems);
 	if (rc) return rc;
 	if (a_elems > 0) {
-		k_eps_solve<<<(unsigned)nb, SOLVE_THREADS, 0, ctx->stream>>>(a);
+		// systems of 65 .. 512 markers: the cluster kernel (matrix in distributed shared memory); smaller ones — usually many of them,
+		// Honami: 128 x 31 — one CTA each
+		int64_t max_dim = 0;
+		for (int64_t b = 0; b < nb; b++) max_dim = first[b + 1] - first[b] > max_dim ? first[b + 1] - first[b] : max_dim;
+		const size_t smem = sizeof(double) * (((size_t)((max_dim + EC_CLUSTER - 1) / EC_CLUSTER)) * (size_t)max_dim + 2 * (size_t)(max_dim + 2) + 2 * (size_t)max_dim);
+		if (max_dim > 64 && max_dim <= 512 && smem <= 200 * 1024 && ctx->cfg.tune != 40) {
+			LIFE_CUDA(ctx, cudaFuncSetAttribute(k_eps_solve_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+			k_eps_solve_cluster<<<(unsigned)(nb * EC_CLUSTER), EC_THREADS, smem, ctx->stream>>>(a);
+		} else {
+			k_eps_solve<<<(unsigned)nb, SOLVE_THREADS, 0, ctx->stream>>>(a);
+		}
 		ctx->launches++;
 		LIFE_CUDA(ctx, cudaGetLastError());
 	}

@@ -45,8 +45,9 @@ __device__ __forceinline__ double equilibrium(double rho, double ux, double uy, 
 	const double cx = (double)kCx[v], cy = (double)kCy[v];
 	const double w = v == 0 ? W0 : (v < 5 ? W1 : W2);
 	if (COLL == COLL_CM) {
-		return 0.25 * rho * w * (9.0 * cx * cx * ux * ux + 6.0 * cx * ux - 3.0 * ux * ux + 2.0) *
-		       (9.0 * cy * cy * uy * uy + 6.0 * cy * uy - 3.0 * uy * uy + 2.0);
+		// association of the reference's 9.0 * SQ(cx) * SQ(ux) + 6.0 * cx * ux - 3.0 * SQ(ux) + 2.0
+		return 0.25 * rho * w * (9.0 * (cx * cx) * (ux * ux) + 6.0 * cx * ux - 3.0 * (ux * ux) + 2.0) *
+		       (9.0 * (cy * cy) * (uy * uy) + 6.0 * cy * uy - 3.0 * (uy * uy) + 2.0);
 	} else {
 		return rho * w * (1.0 + 3.0 * (cx * ux + cy * uy) +
 		                  4.5 * (ux * ux * (cx * cx - 1.0 / 3.0) + uy * uy * (cy * cy - 1.0 / 3.0)) +
@@ -176,6 +177,113 @@ __device__ __forceinline__ void collide_cm(const double (&f)[NV], double sum, do
 	o[6] = p - q;
 	o[7] = r + t;
 	o[8] = r - t;
+}
+
+
+// Central moments in the REFERENCE'S OPERATION ORDER (cfg.exact; same compilation rules as collide_bgk_ref): the pre-collision
+// moments as the v-ascending sums of src/Grid.cpp:113-122, the post-collision moments of :125-133, and the nine back-transform
+// polynomials of :143-223 with every sum and product associated as the reference's expression parses (left to right, its
+// parentheses kept).  x = ux, y = uy, xx = ux*ux, yy = uy*uy; k0..k8 as in the reference.
+__device__ __forceinline__ void collide_cm_ref(const double (&f)[NV], double rho, double x, double y, double Fx, double Fy, double omega,
+                                               double (&o)[NV]) {
+	double k4Pre = 0.0, k5Pre = 0.0;
+#pragma unroll
+	for (int v = 0; v < NV; v++) {
+		const double cx = LIFE_CX(v) - x, cy = LIFE_CY(v) - y;
+		k4Pre += f[v] * ((cx * cx) - (cy * cy));
+		k5Pre += f[v] * cx * cy;
+	}
+	const double k0 = rho;
+	const double k1 = 0.5 * Fx;
+	const double k2 = 0.5 * Fy;
+	const double k3 = 2.0 * rho * CS2;
+	const double k4 = (1.0 - omega) * k4Pre;
+	const double k5 = (1.0 - omega) * k5Pre;
+	const double k6 = 0.5 * Fy * CS2;
+	const double k7 = 0.5 * Fx * CS2;
+	const double k8 = rho * CS4;
+	const double xx = x * x, yy = y * y;
+	o[0] = (xx * yy - xx - yy + 1.0) * k0
+	     + (2.0 * x * yy - 2.0 * x) * k1
+	     + (2.0 * y * xx - 2.0 * y) * k2
+	     + (0.5 * xx + 0.5 * yy - 1.0) * k3
+	     + (0.5 * yy - 0.5 * xx) * k4
+	     + 4.0 * x * y * k5
+	     + 2.0 * y * k6
+	     + 2.0 * x * k7
+	     + k8;
+	o[1] = (0.5 * xx - 0.5 * (xx * yy) - 0.5 * (x * yy) + 0.5 * x) * k0
+	     + (x - x * yy - 0.5 * yy + 0.5) * k1
+	     + (-y * xx - y * x) * k2
+	     + (-0.25 * xx - 0.25 * x - 0.25 * yy + 0.25) * k3
+	     + (0.25 * xx + 0.25 * x - 0.25 * yy + 0.25) * k4
+	     + (-y - 2.0 * x * y) * k5
+	     + (-y) * k6
+	     + (-x - 0.5) * k7
+	     - 0.5 * k8;
+	o[2] = (-0.5 * (xx * yy) + 0.5 * xx + 0.5 * (x * yy) - 0.5 * x) * k0
+	     + (x - x * yy + 0.5 * yy - 0.5) * k1
+	     + (-y * xx + y * x) * k2
+	     + (-0.25 * xx + 0.25 * x - 0.25 * yy + 0.25) * k3
+	     + (0.25 * xx - 0.25 * x - 0.25 * yy + 0.25) * k4
+	     + (y - 2.0 * x * y) * k5
+	     + (-y) * k6
+	     + (0.5 - x) * k7
+	     - 0.5 * k8;
+	o[3] = (0.5 * yy - 0.5 * (xx * y) - 0.5 * (xx * yy) + 0.5 * y) * k0
+	     + (-x * yy - x * y) * k1
+	     + (y - xx * y - 0.5 * xx + 0.5) * k2
+	     + (-0.25 * xx - 0.25 * yy - 0.25 * y + 0.25) * k3
+	     + (0.25 * xx - 0.25 * yy - 0.25 * y - 0.25) * k4
+	     + (-x - 2.0 * x * y) * k5
+	     + (-y - 0.5) * k6
+	     + (-x) * k7
+	     - 0.5 * k8;
+	o[4] = (-0.5 * (xx * yy) + 0.5 * (xx * y) + 0.5 * yy - 0.5 * y) * k0
+	     + (-x * yy + x * y) * k1
+	     + (y - xx * y + 0.5 * xx - 0.5) * k2
+	     + (-0.25 * xx - 0.25 * yy + 0.25 * y + 0.25) * k3
+	     + (0.25 * xx - 0.25 * yy + 0.25 * y - 0.25) * k4
+	     + (x - 2.0 * x * y) * k5
+	     + (0.5 - y) * k6
+	     + (-x) * k7
+	     - 0.5 * k8;
+	o[5] = (0.25 * (xx * yy) + 0.25 * (xx * y) + 0.25 * (x * yy) + 0.25 * (x * y)) * k0
+	     + (0.25 * y + 0.5 * (x * y) + 0.5 * (x * yy) + 0.25 * yy) * k1
+	     + (0.25 * x + 0.5 * (x * y) + 0.5 * (xx * y) + 0.25 * xx) * k2
+	     + (0.125 * xx + 0.125 * x + 0.125 * yy + 0.125 * y) * k3
+	     + (-0.125 * xx - 0.125 * x + 0.125 * yy + 0.125 * y) * k4
+	     + (0.5 * x + 0.5 * y + x * y + 0.25) * k5
+	     + (0.5 * y + 0.25) * k6
+	     + (0.5 * x + 0.25) * k7
+	     + 0.25 * k8;
+	o[6] = (0.25 * (xx * yy) - 0.25 * (xx * y) - 0.25 * (x * yy) + 0.25 * (x * y)) * k0
+	     + (0.25 * y - 0.5 * (x * y) + 0.5 * (x * yy) - 0.25 * yy) * k1
+	     + (0.25 * x - 0.5 * (x * y) + 0.5 * (xx * y) - 0.25 * xx) * k2
+	     + (0.125 * xx - 0.125 * x + 0.125 * yy - 0.125 * y) * k3
+	     + (-0.125 * xx + 0.125 * x + 0.125 * yy - 0.125 * y) * k4
+	     + (x * y - 0.5 * y - 0.5 * x + 0.25) * k5
+	     + (0.5 * y - 0.25) * k6
+	     + (0.5 * x - 0.25) * k7
+	     + 0.25 * k8;
+	o[7] = (0.25 * (xx * yy) - 0.25 * (xx * y) + 0.25 * (x * yy) - 0.25 * (x * y)) * k0
+	     + (0.5 * (x * yy) - 0.5 * (x * y) - 0.25 * y + 0.25 * yy) * k1
+	     + (0.5 * (x * y) - 0.25 * x + 0.5 * (xx * y) - 0.25 * xx) * k2
+	     + (0.125 * xx + 0.125 * x + 0.125 * yy - 0.125 * y) * k3
+	     + (-0.125 * xx - 0.125 * x + 0.125 * yy - 0.125 * y) * k4
+	     + (0.5 * y - 0.5 * x + x * y - 0.25) * k5
+	     + (0.5 * y - 0.25) * k6
+	     + (0.5 * x + 0.25) * k7
+	     + 0.25 * k8;
+	o[8] = (0.25 * (xx * yy) + 0.25 * (xx * y) - 0.25 * (x * yy) - 0.25 * (x * y)) * k0
+	     + (0.5 * (x * y) - 0.25 * y + 0.5 * (x * yy) - 0.25 * yy) * k1
+	     + (0.5 * (xx * y) - 0.5 * (x * y) - 0.25 * x + 0.25 * xx) * k2
+	     + (0.125 * xx - 0.125 * x + 0.125 * yy + 0.125 * y) * k3
+	     + (-0.125 * xx + 0.125 * x + 0.125 * yy + 0.125 * y) * k4
+	     + (0.5 * x - 0.5 * y + x * y - 0.25) * k5
+	     + (0.5 * y + 0.25) * k6
+	     + (0.5 * x - 0.25) * k7
+	     + 0.25 * k8;
 }
 
 }  // namespace life

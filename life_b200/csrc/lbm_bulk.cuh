@@ -83,9 +83,8 @@ __device__ __forceinline__ void node_update(const BulkArgs &a, int64_t idx, cons
 	}
 	constexpr bool HASF = MODE != M_NONE;
 #ifdef LIFE_EXACT
-	// BGK: the reference's own evaluation order, bit for bit.  Central moments: the factored form without FMA contraction
-	// (deterministic, within rounding of the reference's nine expanded polynomials, src/Grid.cpp:143-223).
-	if (COLL == COLL_CM) collide_cm<HASF>(f, sum, mx, my, rho, ux, uy, Fcx, Fcy, a.omega, o);
+	// both operators in the reference's own evaluation order, bit for bit (d2q9.cuh)
+	if (COLL == COLL_CM) collide_cm_ref(f, rho, ux, uy, Fcx, Fcy, a.omega, o);
 	else collide_bgk_ref<HASF>(f, rho, ux, uy, Fcx, Fcy, a.omega, o);
 #else
 	if (COLL == COLL_CM) collide_cm<HASF>(f, sum, mx, my, rho, ux, uy, Fcx, Fcy, a.omega, o);

@@ -41,7 +41,7 @@ def test_inplace_fields_match_oracle_and_two_buffer_layout(case):
     b.close()
 
 
-@pytest.mark.parametrize("case", [c for c in LBM_CASES if not int(K.golden(c)["central_moments"])])
+@pytest.mark.parametrize("case", LBM_CASES)
 def test_inplace_exact_mode_is_bitwise_the_reference(case):
     from life_b200 import capi
     g = K.golden(case)
@@ -53,7 +53,8 @@ def test_inplace_exact_mode_is_bitwise_the_reference(case):
     o.step(N)
     st = a.download_state()
     for name in ("rho", "u", "f"):
-        assert np.array_equal(st[name], o.get(name)), (case, name, K.rel_l2(st[name], o.get(name)))
+        if not int(g["central_moments"]):      # (the oracle's central-moments path is factored: only the fixtures are the reference's bits)
+            assert np.array_equal(st[name], o.get(name)), (case, name, K.rel_l2(st[name], o.get(name)))
         assert np.array_equal(K.sampled(st[name], g), g[name]), (case, "golden " + name)
     a.close()
 

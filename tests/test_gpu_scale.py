@@ -23,7 +23,7 @@ def _cavity_config(capi, N, collision, **kw):
                        Dt=(1.0 / np.sqrt(3.0)) ** 2 * Dx * Dx * 0.5 / nu_p, **kw)
 
 
-@pytest.mark.parametrize("collision,exact", [("bgk", 0), ("bgk", 1), ("cm", 0)], ids=["bgk-fast", "bgk-exact", "cm-fast"])
+@pytest.mark.parametrize("collision,exact", [("bgk", 0), ("bgk", 1), ("cm", 0), ("cm", 1)], ids=["bgk-fast", "bgk-exact", "cm-fast", "cm-exact"])
 def test_cavity_4096_against_the_compiled_reference(collision, exact):
     from life_b200 import capi
     from oracle import refharness as RH

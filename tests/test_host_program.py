@@ -163,13 +163,14 @@ def _diff_r(ref_dir, new_dir):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("variant", ["default", "host-eps", "host-io", "inplace"])
-@pytest.mark.parametrize("case", [c for c in EXAMPLES if c != "LidDrivenCavity"])
+@pytest.mark.parametrize("case", EXAMPLES)
 def test_program_in_exact_mode_is_bitwise_the_reference(case, variant, tmp_path):
     """The reference's own regression protocol, unrelaxed: LIFE_b200 with LIFE_B200_EXACT=1 (cfg.exact: the step in the
     reference's operation order, kernels of namespace life::exact) against LIFE_ref — 500 steps, TurekHron twice (restart), then
     `diff -r Results` excluding Log.out must find NO differing file: every .vti / .vtp, Fluid / IBM / FEM.restart,
     TotalForces.out, TipPositions.out ... byte for byte, with the live FEM + Aitken sub-iteration loop in between
-    (TurekHron, InvertedFlag, Honami, PELskin).  All six cases are BGK (LidDrivenCavity is central moments, tested at 1e-10)."""
+    (TurekHron, InvertedFlag, Honami, PELskin).  Six cases are BGK, LidDrivenCavity is central moments (the reference's nine
+    expanded polynomials restated term by term, d2q9.cuh: collide_cm_ref): all seven examples of the reference."""
     if not (_have(case, "LIFE_b200") and _have(case, "LIFE_ref")):
         pytest.skip("life_b200/host/_build/%s not built (make -C life_b200/host needs /root/reference)" % case)
     if variant not in ("default", "inplace") and case not in ("ChannelFlow", "TurekHron", "PELskin"):

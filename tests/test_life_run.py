@@ -63,7 +63,7 @@ def test_life_run_rejects_a_bad_case_file(tmp_path):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("gpus", [1, 2, 4])
-@pytest.mark.parametrize("case,exact", [("ChannelFlow", 1), ("ChannelFlow", 0), ("LidDrivenCavity", 0)])
+@pytest.mark.parametrize("case,exact", [("ChannelFlow", 1), ("ChannelFlow", 0), ("LidDrivenCavity", 1), ("LidDrivenCavity", 0)])
 def test_life_run_reproduces_the_reference_program(case, exact, gpus, tmp_path):
     if not (os.path.exists(EXE) and os.path.exists(os.path.join(HOST, case, "LIFE_ref"))):
         pytest.skip("life_b200/host/_build not built")

@@ -93,8 +93,9 @@ typedef struct life_config {
 	int32_t exact;             /* 1: the LBM step in the REFERENCE'S OPERATION ORDER without FMA contraction — BGK collision, macroscopic,
 	                              regularised / convective boundaries, the outlet mean as a serial sum in j order (src/Grid.cpp:237-299,
 	                              :387-495) — so that fields, marker forces and files equal the reference's g++ build bit for bit (the
-	                              reference's own regression protocol is `diff -r`, testing/run-tests.sh:100).  ~3x the arithmetic of the
-	                              default factored collision.  Central moments: same factored form, FMA-free (deterministic, not bitwise). */
+	                              reference's own regression protocol is `diff -r`, testing/run-tests.sh:100).  Both collision operators
+	                              (central moments: the nine expanded polynomials of src/Grid.cpp:143-223); ~3-4x the arithmetic of the
+	                              default factored collisions. */
 	int32_t inplace;           /* 1: ONE population buffer (72 B/node resident instead of 144): the sweep collides in place and streaming is
 	                              implicit — population v of node n lives at plane element (n - t_steps * shift_v) mod S, shift_v = cx * pitch + cy,
 	                              so "pushing" it to its neighbour is an offset update, not a data movement (csrc/lbm_bulk.cu: k_bulk_shift).

@@ -419,7 +419,7 @@ int life_step(life_ctx *ctx, int32_t t) {
 	auto bulk = exact ? launch_bulk_exact : launch_bulk;
 	// cfg.inplace: what the boundary kernel needs of the pre-sweep state is saved first; after the sweep the layout offsets advance
 	// (that is the streaming), and ring / halo / boundary work on the advanced layout of the same buffer
-	if (ctx->inplace && (rc = exact ? launch_bc_capture_exact(ctx, sc) : launch_bc_capture(ctx, sc))) return rc;
+	if ((ctx->inplace || ctx->wom_field) && (rc = exact ? launch_bc_capture_exact(ctx, sc) : launch_bc_capture(ctx, sc))) return rc;
 	auto advance = [&]() {
 		if (!ctx->inplace) return;
 		static const int cx[9] = {0, 1, -1, 0, 0, 1, -1, 1, -1}, cy[9] = {0, 0, 0, 1, -1, 1, -1, -1, 1};

@@ -25,6 +25,7 @@ struct FemState {
 	int n_bodies = 0;
 	std::vector<Body> h_bodies;          // host copies of the views (device pointers inside)
 	std::vector<int> marker_first;       // CSR over bodies into marker ids
+	int max_dof = 0;                     // largest n_dof of any body: sizes the shared-memory work space of k_fem<FEM_DYNAMIC>
 	Body *d_bodies = nullptr;
 	double *d_arena = nullptr;
 	int *d_ints = nullptr;
@@ -35,12 +36,31 @@ struct FemState {
 
 enum { FEM_DYNAMIC = 0, FEM_PREDICT = 1, FEM_RELAX = 2 };
 
+constexpr int FEM_THREADS = 128;
+
 template <int OP>
-__global__ void __launch_bounds__(64) k_fem(const Body *__restrict__ bodies, const int *__restrict__ mfirst, const int *__restrict__ mids,
-                                            const double *__restrict__ force, const double *__restrict__ eps, double *pos, double *vel,
-                                            int t, double relax, double *results) {
+__global__ void __launch_bounds__(FEM_THREADS) k_fem(const Body *__restrict__ bodies, const int *__restrict__ mfirst, const int *__restrict__ mids,
+                                                     const double *__restrict__ force, const double *__restrict__ eps, double *pos, double *vel,
+                                                     int t, double relax, double *results) {
 	__shared__ Body b;
-	if (threadIdx.x == 0) b = bodies[blockIdx.x];
+	extern __shared__ double fem_sm[];
+	if (threadIdx.x == 0) {
+		b = bodies[blockIdx.x];
+		if (OP == FEM_DYNAMIC) {
+			// The Newton-Raphson work space — dense M and K (dim^2 each), the vectors of the Newmark system, the pivots — lives in shared
+			// memory for the duration of the call: the LU is a chain of ~5 barriers per column, and every one of them used to wait for
+			// an L2 round trip.  Nothing in it survives the call (M, K are rebuilt by every iteration; R, F, delU are per call).
+			const size_t d = (size_t)b.n_dof;
+			double *p = fem_sm;
+			b.M = p; p += d * d;
+			b.K = p; p += d * d;
+			b.R = p; p += d;
+			b.F = p; p += d;
+			b.delU = p; p += d;
+			b.work = p; p += d;
+			b.piv = reinterpret_cast<int *>(p);
+		}
+	}
 	__syncthreads();
 	const Lane l{(int)threadIdx.x, (int)blockDim.x};
 	const int *marker = mids + mfirst[blockIdx.x];
@@ -58,7 +78,7 @@ __global__ void __launch_bounds__(64) k_fem(const Body *__restrict__ bodies, con
 }
 
 // IBMNodeClass::computeDs (src/IBMNode.cpp:182-204) of the markers of every flexible body, after the solver moved them
-__global__ void __launch_bounds__(64) k_fem_ds(const Body *__restrict__ bodies, const int *__restrict__ mfirst, const int *__restrict__ mids,
+__global__ void __launch_bounds__(FEM_THREADS) k_fem_ds(const Body *__restrict__ bodies, const int *__restrict__ mfirst, const int *__restrict__ mids,
                                                const double *__restrict__ pos, double Dx, double *ds) {
 	__shared__ Body b;
 	if (threadIdx.x == 0) b = bodies[blockIdx.x];
@@ -85,8 +105,15 @@ static int fem_ready(life_ctx *ctx, const char *who) {
 template <int OP>
 static int fem_launch(life_ctx *ctx, int t, double relax) {
 	FemState *f = ctx->fem;
-	k_fem<OP><<<(unsigned)f->n_bodies, 64, 0, ctx->stream>>>(f->d_bodies, f->d_marker_first, f->d_marker_ids, ctx->mk.force, ctx->mk.eps,
-	                                                         ctx->mk.pos, ctx->mk.vel, t, relax, f->d_results);
+	size_t smem = 0;
+	if (OP == FEM_DYNAMIC) {
+		const size_t d = (size_t)f->max_dof;
+		smem = sizeof(double) * (2 * d * d + 4 * d) + sizeof(int) * d + 16;
+		if (smem > 200 * 1024) return fail(ctx, LIFE_E_ARG, "life_fem_dynamic: a body has too many degrees of freedom for the shared-memory work space");
+		LIFE_CUDA(ctx, cudaFuncSetAttribute(k_fem<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	}
+	k_fem<OP><<<(unsigned)f->n_bodies, FEM_THREADS, smem, ctx->stream>>>(f->d_bodies, f->d_marker_first, f->d_marker_ids, ctx->mk.force, ctx->mk.eps,
+	                                                                     ctx->mk.pos, ctx->mk.vel, t, relax, f->d_results);
 	ctx->launches++;
 	LIFE_CUDA(ctx, cudaGetLastError());
 	return LIFE_OK;
@@ -148,6 +175,7 @@ static int fem_create_impl(life_ctx *ctx, int32_t n_bodies, const life_fem_body 
 		Body &b = f->h_bodies[(size_t)k];
 		const int n = d.n_nodes, ne = n - 1, dim = 3 * n, nmap = d.map_first[ne];
 		b.n_nodes = n; b.n_el = ne; b.n_dof = dim; b.n_bc = d.n_bc; b.n_ibm = d.n_markers;
+		if (dim > f->max_dof) f->max_dof = dim;
 		b.alpha = d.alpha; b.delta = d.delta; b.Dt = ctx->cfg.Dt; b.Dm = ctx->cfg.Dm; b.gravityX = d.gravity_x; b.gravityY = d.gravity_y; b.ref_L = d.ref_L;
 		double *h, *hL0, *hA, *hI, *hE, *hrho, *hM, *hK;
 		int *g;
@@ -278,7 +306,7 @@ int life_fsi_move(life_ctx *ctx, int32_t t, int32_t sub_it, double relax) {
 	if (rc) return rc;
 	if ((rc = ibm_refresh_supports(ctx))) return rc;
 	FemState *f = ctx->fem;
-	k_fem_ds<<<(unsigned)f->n_bodies, 64, 0, ctx->stream>>>(f->d_bodies, f->d_marker_first, f->d_marker_ids, ctx->mk.pos, ctx->cfg.Dx, ctx->mk.ds);
+	k_fem_ds<<<(unsigned)f->n_bodies, FEM_THREADS, 0, ctx->stream>>>(f->d_bodies, f->d_marker_first, f->d_marker_ids, ctx->mk.pos, ctx->cfg.Dx, ctx->mk.ds);
 	ctx->launches++;
 	LIFE_CUDA(ctx, cudaGetLastError());
 	return LIFE_OK;

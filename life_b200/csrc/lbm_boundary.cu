@@ -155,7 +155,9 @@ int launch_bc_capture_exact(life_ctx *ctx, const StepScalars &sc) {
 #else
 int launch_bc_capture(life_ctx *ctx, const StepScalars &sc) {
 #endif
-	if (!ctx->inplace || ctx->n_bc == 0) return LIFE_OK;
+	// also with two buffers when force_xy is a field the sweep rewrites (Womersley with gravity): the retained normal velocity of a
+	// pressure corner belongs to the PREVIOUS step's force (src/Grid.cpp:356-369), which is gone after the sweep
+	if (!(ctx->inplace || ctx->wom_field) || ctx->n_bc == 0) return LIFE_OK;
 	const bool needed = ctx->cfg.wall_right == LIFE_CONVECTIVE || ctx->cfg.wall_left == LIFE_PRESSURE || ctx->cfg.wall_right == LIFE_PRESSURE ||
 	                    ctx->cfg.wall_bottom == LIFE_PRESSURE || ctx->cfg.wall_top == LIFE_PRESSURE;
 	if (!needed) return LIFE_OK;

@@ -248,6 +248,8 @@ static inline BcArgs make_bc_args(life_ctx *ctx, const StepScalars &sc) {
 		a.fprev = nullptr; a.f = ctx->fA;
 		a.ps = ctx->shift;
 		a.captured = ctx->bc_prev;
+	} else if (ctx->wom_field && ctx->bc_prev) {
+		a.captured = ctx->bc_prev;      // force_xy field rewritten by the sweep: pre-sweep u_n of pressure corners saved by k_bc_capture
 	}
 	a.stored = ctx->stored_macro_valid ? ctx->macro : nullptr;
 	a.L = ctx->L;

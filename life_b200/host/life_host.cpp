@@ -505,7 +505,7 @@ void ObjectsClass::objectKernel() {
 	const int64_t nb = (int64_t)dev.grp_first.size() - 1;
 	int64_t largest = 0;
 	for (int64_t b = 0; b < nb; b++) largest = std::max(largest, dev.grp_first[b + 1] - dev.grp_first[b]);
-	static const int lu_limit = [] { const char *e = std::getenv("LIFE_B200_DEVICE_LU_MAX"); return e ? std::atoi(e) : 512; }();      // (> 64 markers: the cluster LU of csrc/ibm_eps.cu)
+	static const int lu_limit = [] { const char *e = std::getenv("LIFE_B200_DEVICE_LU_MAX"); return e ? std::atoi(e) : 96; }();       // larger systems: matrix from the device, the host's LAPACK (measured faster than the cluster LU of csrc/ibm_eps.cu at n = 132, equal at 310; LIFE_B200_DEVICE_LU_MAX=512 keeps them on the device)
 	subIt = 0;
 	const int MAXIT = 20;
 	double sums[3] = {0, 0, 0};

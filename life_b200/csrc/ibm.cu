@@ -391,9 +391,7 @@ __global__ void __launch_bounds__(128) k_spread_atomic(const SpreadArgs a) {
 //                  reference's `omp ordered` loop (src/Objects.cpp:130-139; one contribution per marker and site) — adds them up from
 //                  0.0 exactly as the reference's `+=` does, writes force_ibm and the span mask, and resets the head to -1.
 // No floating-point atomics, no sort over all entries, no search: the only dependent chain is the list walk.
-__global__ void __launch_bounds__(256) k_site_lists(const SpreadArgs a) {
-	const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (e >= a.n * SUPP) return;
+__device__ __forceinline__ void site_list_push(const SpreadArgs &a, const int64_t e) {
 	const int64_t m = e / SUPP;
 	if ((int)(e - m * SUPP) >= a.scount[m]) return;
 	const int64_t il = (int64_t)a.sidx[e] - a.i_begin;
@@ -401,9 +399,7 @@ __global__ void __launch_bounds__(256) k_site_lists(const SpreadArgs a) {
 	a.next[e] = atomicExch(a.head + a.L.node(il, a.sjdx[e]), (int32_t)e);
 }
 
-__global__ void __launch_bounds__(256) k_spread_ordered(const SpreadArgs a) {
-	const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (e >= a.n * SUPP) return;
+__device__ __forceinline__ void site_owner_sum(const SpreadArgs &a, const int64_t e) {
 	const int64_t m = e / SUPP;
 	if ((int)(e - m * SUPP) >= a.scount[m]) return;
 	const int j = a.sjdx[e];
@@ -436,6 +432,26 @@ __global__ void __launch_bounds__(256) k_spread_ordered(const SpreadArgs a) {
 	a.head[idx] = -1;                               // empty again for the next spread
 }
 
+__global__ void __launch_bounds__(256) k_site_lists(const SpreadArgs a) {
+	const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (e < a.n * SUPP) site_list_push(a, e);
+}
+
+__global__ void __launch_bounds__(256) k_spread_ordered(const SpreadArgs a) {
+	const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (e < a.n * SUPP) site_owner_sum(a, e);
+}
+
+// the same two phases in ONE launch of one CTA, for the marker counts of the examples (<= 4096 markers = 36 864 entries): the barrier
+// between building the lists and walking them is a __syncthreads instead of a kernel boundary
+constexpr int SPREAD_ONE_CTA_MAX = 4096;
+__global__ void __launch_bounds__(1024) k_spread_ordered_one_cta(const SpreadArgs a) {
+	const int64_t n = a.n * SUPP;
+	for (int64_t e = threadIdx.x; e < n; e += blockDim.x) site_list_push(a, e);
+	__syncthreads();      // (orders this CTA's global-memory accesses too)
+	for (int64_t e = threadIdx.x; e < n; e += blockDim.x) site_owner_sum(a, e);
+}
+
 int ibm_spread(life_ctx *ctx) {
 	int rc;
 	if ((rc = ensure_fibm(ctx))) return rc;
@@ -458,10 +474,15 @@ int ibm_spread(life_ctx *ctx) {
 			LIFE_CUDA(ctx, cudaMemsetAsync(ctx->cell_head, 0xff, sizeof(int32_t) * ctx->L.S, ctx->stream));
 		}
 		a.head = ctx->cell_head;
-		const unsigned eb = (unsigned)((m.n * SUPP + 255) / 256);
-		k_site_lists<<<eb, 256, 0, ctx->stream>>>(a);
-		k_spread_ordered<<<eb, 256, 0, ctx->stream>>>(a);
-		ctx->launches += 2;
+		if (m.n <= SPREAD_ONE_CTA_MAX && ctx->cfg.tune != 41) {
+			k_spread_ordered_one_cta<<<1, 1024, 0, ctx->stream>>>(a);
+			ctx->launches++;
+		} else {
+			const unsigned eb = (unsigned)((m.n * SUPP + 255) / 256);
+			k_site_lists<<<eb, 256, 0, ctx->stream>>>(a);
+			k_spread_ordered<<<eb, 256, 0, ctx->stream>>>(a);
+			ctx->launches += 2;
+		}
 	} else {
 		const int64_t threads = m.n * 32;
 		k_spread_atomic<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(a);

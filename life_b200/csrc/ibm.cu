@@ -442,16 +442,6 @@ __global__ void __launch_bounds__(256) k_spread_ordered(const SpreadArgs a) {
 	if (e < a.n * SUPP) site_owner_sum(a, e);
 }
 
-// the same two phases in ONE launch of one CTA, for the marker counts of the examples (<= 4096 markers = 36 864 entries): the barrier
-// between building the lists and walking them is a __syncthreads instead of a kernel boundary
-constexpr int SPREAD_ONE_CTA_MAX = 4096;
-__global__ void __launch_bounds__(1024) k_spread_ordered_one_cta(const SpreadArgs a) {
-	const int64_t n = a.n * SUPP;
-	for (int64_t e = threadIdx.x; e < n; e += blockDim.x) site_list_push(a, e);
-	__syncthreads();      // (orders this CTA's global-memory accesses too)
-	for (int64_t e = threadIdx.x; e < n; e += blockDim.x) site_owner_sum(a, e);
-}
-
 int ibm_spread(life_ctx *ctx) {
 	int rc;
 	if ((rc = ensure_fibm(ctx))) return rc;
@@ -474,15 +464,12 @@ int ibm_spread(life_ctx *ctx) {
 			LIFE_CUDA(ctx, cudaMemsetAsync(ctx->cell_head, 0xff, sizeof(int32_t) * ctx->L.S, ctx->stream));
 		}
 		a.head = ctx->cell_head;
-		if (m.n <= SPREAD_ONE_CTA_MAX && ctx->cfg.tune != 41) {
-			k_spread_ordered_one_cta<<<1, 1024, 0, ctx->stream>>>(a);
-			ctx->launches++;
-		} else {
-			const unsigned eb = (unsigned)((m.n * SUPP + 255) / 256);
-			k_site_lists<<<eb, 256, 0, ctx->stream>>>(a);
-			k_spread_ordered<<<eb, 256, 0, ctx->stream>>>(a);
-			ctx->launches += 2;
-		}
+		// (both phases in one launch of one 1024-thread CTA was tried for example-scale marker counts: 24.9 us against 11.4 us for
+		// these two whole-GPU launches, profiles/r02_ncu_summary.md)
+		const unsigned eb = (unsigned)((m.n * SUPP + 255) / 256);
+		k_site_lists<<<eb, 256, 0, ctx->stream>>>(a);
+		k_spread_ordered<<<eb, 256, 0, ctx->stream>>>(a);
+		ctx->launches += 2;
 	} else {
 		const int64_t threads = m.n * 32;
 		k_spread_atomic<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(a);

@@ -57,6 +57,11 @@ static void free_ctx(life_ctx *ctx) {
 	cudaFree(ctx->scratch); cudaFree(ctx->d_red); cudaFree(ctx->eps_buf); cudaFree(ctx->d_steps);
 	if (ctx->h_steps) cudaFreeHost(ctx->h_steps);
 	if (ctx->ev_steps) cudaEventDestroy(ctx->ev_steps);
+	for (int k = 0; k < 2; k++) {
+		if (ctx->ev_copy[k]) cudaEventDestroy(ctx->ev_copy[k]);
+		if (ctx->ev_kernel[k]) cudaEventDestroy(ctx->ev_kernel[k]);
+	}
+	if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
 	if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
 	for (auto &p : ctx->prof_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
 	if (ctx->ev_edge) cudaEventDestroy(ctx->ev_edge);

@@ -132,8 +132,10 @@ struct life_ctx {
 	life::MarkerBuffers mk;
 	life::IoState *io = nullptr;          // staging, snapshot and worker of the device-fed file paths (lbm_file.cu)
 	life::FemState *fem = nullptr;        // flexible bodies of the device structural solver (fem.cu)
-	double *scratch = nullptr;            // device staging for upload / download
-	size_t scratch_bytes = 0;
+	double *scratch = nullptr;            // device staging for upload / download: two halves, so the PCIe copy of one chunk overlaps
+	size_t scratch_bytes = 0;             // the pack / unpack kernel of the other (copies on copy_stream, kernels on stream)
+	cudaStream_t copy_stream = nullptr;
+	cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_kernel[2] = {nullptr, nullptr};
 	double *d_red = nullptr;              // reduction scratch (max speed etc.)
 	life::StepScalars *d_steps = nullptr, *h_steps = nullptr;   // per-step scalars of a multi-step launch (lbm_small.cu): device + pinned host
 	int32_t steps_cap = 0;

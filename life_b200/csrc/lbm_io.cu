@@ -61,46 +61,78 @@ __global__ void k_pack(double *__restrict__ dst, const double *__restrict__ plan
 
 static int64_t chunk_columns(life_ctx *ctx, int ncomp) {
 	const int64_t per_col = ctx->L.Ny * ncomp;
-	const int64_t target = (int64_t)(256ll << 20) / (int64_t)sizeof(double);   // 256 MiB staging
+	const int64_t target = (int64_t)(128ll << 20) / (int64_t)sizeof(double);   // 128 MiB per staging half
 	int64_t cols = target / per_col;
 	if (cols < 1) cols = 1;
 	if (cols > ctx->L.nxl) cols = ctx->L.nxl;
 	return cols;
 }
 
-// host chunk `h` = columns [il0, il0 + ncols) of a reference-layout array with `ncomp` doubles per node
-int upload_field(life_ctx *ctx, const double *h, double *planes, int ncomp, int64_t il0, int64_t ncols) {
-	const Layout &L = ctx->L;
-	const int64_t cols = chunk_columns(ctx, ncomp);
-	int rc = ensure_scratch(ctx, sizeof(double) * (size_t)(cols * L.Ny * ncomp));
-	if (rc) return rc;
-	for (int64_t c0 = 0; c0 < ncols; c0 += cols) {
-		const int64_t nc = (c0 + cols <= ncols) ? cols : ncols - c0;
-		const int64_t n_elems = nc * L.Ny * ncomp;
-		LIFE_CUDA(ctx, cudaMemcpyAsync(ctx->scratch, h + c0 * L.Ny * ncomp, sizeof(double) * n_elems,
-		                               cudaMemcpyHostToDevice, ctx->stream));
-		k_unpack<<<(unsigned)((n_elems + 255) / 256), 256, 0, ctx->stream>>>(ctx->scratch, planes, L, ncomp, il0 + c0, n_elems);
-		ctx->launches++;
-		LIFE_CUDA(ctx, cudaGetLastError());
+static int ensure_copy_stream(life_ctx *ctx) {
+	if (ctx->copy_stream) return LIFE_OK;
+	LIFE_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+	for (int k = 0; k < 2; k++) {
+		LIFE_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copy[k], cudaEventDisableTiming));
+		LIFE_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_kernel[k], cudaEventDisableTiming));
 	}
 	return LIFE_OK;
 }
 
+// host chunk `h` = columns [il0, il0 + ncols) of a reference-layout array with `ncomp` doubles per node.
+// Double-buffered: chunk k travels over PCIe (copy stream) while chunk k-1 is unpacked into the planes (compute stream).
+int upload_field(life_ctx *ctx, const double *h, double *planes, int ncomp, int64_t il0, int64_t ncols) {
+	const Layout &L = ctx->L;
+	const int64_t cols = chunk_columns(ctx, ncomp);
+	const size_t half = sizeof(double) * (size_t)(cols * L.Ny * ncomp);
+	int rc = ensure_scratch(ctx, 2 * half);
+	if (rc) return rc;
+	if ((rc = ensure_copy_stream(ctx))) return rc;
+	// the staging halves may still be read by kernels enqueued earlier on the compute stream
+	LIFE_CUDA(ctx, cudaEventRecord(ctx->ev_kernel[0], ctx->stream));
+	LIFE_CUDA(ctx, cudaEventRecord(ctx->ev_kernel[1], ctx->stream));
+	int k = 0;
+	for (int64_t c0 = 0; c0 < ncols; c0 += cols, k ^= 1) {
+		const int64_t nc = (c0 + cols <= ncols) ? cols : ncols - c0;
+		const int64_t n_elems = nc * L.Ny * ncomp;
+		double *stage = reinterpret_cast<double *>(reinterpret_cast<char *>(ctx->scratch) + (k ? half : 0));
+		LIFE_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_kernel[k], 0));      // the kernel that last read this half is done
+		LIFE_CUDA(ctx, cudaMemcpyAsync(stage, h + c0 * L.Ny * ncomp, sizeof(double) * n_elems, cudaMemcpyHostToDevice, ctx->copy_stream));
+		LIFE_CUDA(ctx, cudaEventRecord(ctx->ev_copy[k], ctx->copy_stream));
+		LIFE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[k], 0));
+		k_unpack<<<(unsigned)((n_elems + 255) / 256), 256, 0, ctx->stream>>>(stage, planes, L, ncomp, il0 + c0, n_elems);
+		ctx->launches++;
+		LIFE_CUDA(ctx, cudaGetLastError());
+		LIFE_CUDA(ctx, cudaEventRecord(ctx->ev_kernel[k], ctx->stream));
+	}
+	return LIFE_OK;
+}
+
+// Double-buffered the other way round: chunk k is packed (compute stream) while chunk k-1 travels to the host (copy stream).
 int download_field(life_ctx *ctx, double *h, const double *planes, int ncomp, int64_t il0, int64_t ncols, const PopShift *ps) {
 	const Layout &L = ctx->L;
 	const PopShift shift = ps ? *ps : PopShift{};
 	const int64_t cols = chunk_columns(ctx, ncomp);
-	int rc = ensure_scratch(ctx, sizeof(double) * (size_t)(cols * L.Ny * ncomp));
+	const size_t half = sizeof(double) * (size_t)(cols * L.Ny * ncomp);
+	int rc = ensure_scratch(ctx, 2 * half);
 	if (rc) return rc;
-	for (int64_t c0 = 0; c0 < ncols; c0 += cols) {
+	if ((rc = ensure_copy_stream(ctx))) return rc;
+	LIFE_CUDA(ctx, cudaEventRecord(ctx->ev_copy[0], ctx->copy_stream));
+	LIFE_CUDA(ctx, cudaEventRecord(ctx->ev_copy[1], ctx->copy_stream));
+	int k = 0;
+	for (int64_t c0 = 0; c0 < ncols; c0 += cols, k ^= 1) {
 		const int64_t nc = (c0 + cols <= ncols) ? cols : ncols - c0;
 		const int64_t n_elems = nc * L.Ny * ncomp;
-		k_pack<<<(unsigned)((n_elems + 255) / 256), 256, 0, ctx->stream>>>(ctx->scratch, planes, L, ncomp, il0 + c0, n_elems, shift);
+		double *stage = reinterpret_cast<double *>(reinterpret_cast<char *>(ctx->scratch) + (k ? half : 0));
+		LIFE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[k], 0));             // the copy that last read this half is done
+		k_pack<<<(unsigned)((n_elems + 255) / 256), 256, 0, ctx->stream>>>(stage, planes, L, ncomp, il0 + c0, n_elems, shift);
 		ctx->launches++;
 		LIFE_CUDA(ctx, cudaGetLastError());
-		LIFE_CUDA(ctx, cudaMemcpyAsync(h + c0 * L.Ny * ncomp, ctx->scratch, sizeof(double) * n_elems,
-		                               cudaMemcpyDeviceToHost, ctx->stream));
+		LIFE_CUDA(ctx, cudaEventRecord(ctx->ev_kernel[k], ctx->stream));
+		LIFE_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_kernel[k], 0));
+		LIFE_CUDA(ctx, cudaMemcpyAsync(h + c0 * L.Ny * ncomp, stage, sizeof(double) * n_elems, cudaMemcpyDeviceToHost, ctx->copy_stream));
+		LIFE_CUDA(ctx, cudaEventRecord(ctx->ev_copy[k], ctx->copy_stream));
 	}
+	LIFE_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
 	LIFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	return LIFE_OK;
 }

@@ -199,6 +199,9 @@ int launch_macro(life_ctx *ctx, double *out_planes, int64_t il0, int64_t ncols) 
 // holding a NaN speed (i-major order = the order the reference's double loop meets them), ~0 if none.
 // Persistent blocks stride over (column, 512-row tile) pairs; each thread handles two adjacent rows with 16-byte loads, like the
 // bulk sweep, so the scan runs at the HBM rate of its 72 B per node.
+// PATH 0: uploaded macroscopics; 1: forces / shifted layout (generic node_macro); 2: force-free plain layout, 16-byte loads.
+// Separate instantiations: the generic path's registers must not cost the common force-free scan its occupancy.
+template <int PATH>
 __global__ void __launch_bounds__(256) k_max_speed(const MacroArgs a, const double *stored, int64_t i_begin,
                                                    unsigned long long *red) {
 	__shared__ unsigned long long smax[256], snan[256];
@@ -212,10 +215,10 @@ __global__ void __launch_bounds__(256) k_max_speed(const MacroArgs a, const doub
 		const int64_t idx = a.L.node(il, j);      // even row offset: 16-byte aligned
 		const bool two = j + 1 < a.L.Ny;
 		double ux[2], uy[2];
-		if (stored) {
+		if (PATH == 0) {
 			ux[0] = stored[a.L.S + idx]; uy[0] = stored[2 * a.L.S + idx];
 			ux[1] = two ? stored[a.L.S + idx + 1] : 0.0; uy[1] = two ? stored[2 * a.L.S + idx + 1] : 0.0;
-		} else if (a.fxy_mode == FXY_FIELD || a.fibm || a.shifted) {
+		} else if (PATH == 1) {
 			double rho;
 			node_macro(a, idx, rho, ux[0], uy[0]);
 			if (two) node_macro(a, idx + 1, rho, ux[1], uy[1]);
@@ -267,9 +270,23 @@ int launch_max_speed(life_ctx *ctx, double *vmax, int32_t *has_nan, int64_t *nan
 	LIFE_CUDA(ctx, cudaMemcpyAsync(ctx->d_red, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
 	MacroArgs a = macro_args(ctx);
 	int64_t blocks = ((a.L.Ny + 511) / 512) * a.L.nxl;
-	if (blocks > 148 * 8) blocks = 148 * 8;      // persistent: 8 resident blocks per SM
-	k_max_speed<<<(unsigned)blocks, 256, 0, ctx->stream>>>(a, ctx->stored_macro_valid ? ctx->macro : nullptr, ctx->i_begin,
-	                                                      reinterpret_cast<unsigned long long *>(ctx->d_red));
+	const int path = ctx->stored_macro_valid ? 0 : ((a.fxy_mode == FXY_FIELD || a.fibm || a.shifted) ? 1 : 2);
+	// persistent: exactly one wave of resident blocks (a fixed 8 per SM used to run 1.6 waves at the kernel's real occupancy)
+	static int per_sm[3] = {0, 0, 0};
+	if (per_sm[path] == 0) {
+		cudaError_t e = path == 0 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], k_max_speed<0>, 256, 0)
+		              : path == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], k_max_speed<1>, 256, 0)
+		                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[2], k_max_speed<2>, 256, 0);
+		if (e != cudaSuccess || per_sm[path] < 1) per_sm[path] = 4;
+	}
+	int sms = 148;
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+	if (blocks > (int64_t)sms * per_sm[path]) blocks = (int64_t)sms * per_sm[path];
+	unsigned long long *red = reinterpret_cast<unsigned long long *>(ctx->d_red);
+	const double *stored = ctx->stored_macro_valid ? ctx->macro : nullptr;
+	if (path == 0) k_max_speed<0><<<(unsigned)blocks, 256, 0, ctx->stream>>>(a, stored, ctx->i_begin, red);
+	else if (path == 1) k_max_speed<1><<<(unsigned)blocks, 256, 0, ctx->stream>>>(a, stored, ctx->i_begin, red);
+	else k_max_speed<2><<<(unsigned)blocks, 256, 0, ctx->stream>>>(a, stored, ctx->i_begin, red);
 	ctx->launches++;
 	LIFE_CUDA(ctx, cudaGetLastError());
 	if (ctx->comm) {

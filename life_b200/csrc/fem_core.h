@@ -253,6 +253,22 @@ FEM_FN void solve_system(const Body &b, Lane l) {
 	for (int i = l.tid; i < dim; i += l.n) x[i] = i < o ? 0.0 : b.F[i];
 	FEM_SYNC();
 	for (int k = 0; k < n; k++) {
+#if defined(__CUDA_ARCH__)
+		if (l.tid < 32) {   // pivot: largest |A[i][k]|, i >= k (first one wins, as idamax) — one warp, a shuffle reduction
+			double best = -1.0;
+			int p = k;
+			for (int i = k + l.tid; i < n; i += 32) {
+				const double v = fabs(A[(o + i) * dim + o + k]);
+				if (v > best) { best = v; p = i; }
+			}
+			for (int w = 16; w > 0; w >>= 1) {
+				const double ob = __shfl_xor_sync(0xffffffffu, best, w);
+				const int op = __shfl_xor_sync(0xffffffffu, p, w);
+				if (ob > best || (ob == best && op < p)) { best = ob; p = op; }
+			}
+			if (l.tid == 0) b.piv[k] = p;
+		}
+#else
 		if (l.tid == 0) {   // pivot: largest |A[i][k]|, i >= k (first one wins, as idamax)
 			int p = k;
 			double best = fabs(A[(o + k) * dim + o + k]);
@@ -262,6 +278,7 @@ FEM_FN void solve_system(const Body &b, Lane l) {
 			}
 			b.piv[k] = p;
 		}
+#endif
 		FEM_SYNC();
 		const int p = b.piv[k];
 		if (p != k) {

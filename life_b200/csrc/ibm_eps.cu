@@ -49,6 +49,7 @@ struct EpsArgs {
 	int32_t *piv;              // [total members]
 	double *eps;               // marker array to update
 	int32_t *info;             // != 0: a zero pivot was met (LAPACK's info > 0)
+	int smem_dim;              // k_eps_solve: systems up to this dimension are factorised in shared memory (0: none)
 };
 
 __global__ void __launch_bounds__(256) k_eps_assemble(const EpsArgs a) {
@@ -101,6 +102,14 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_eps_solve(const EpsArgs a) {
 	double *x = a.x + m0;
 	int32_t *piv = a.piv + m0;
 	const int tid = threadIdx.x, T = blockDim.x;
+	// small systems (the launch provides dim^2 doubles of dynamic shared memory when every system fits): factorise a shared-memory
+	// copy — every elimination step is a chain of barriers, and each used to wait for an L2 round trip
+	extern __shared__ double eps_sm[];
+	if (a.smem_dim >= dim) {
+		for (int e = tid; e < dim * dim; e += T) eps_sm[e] = M[e];
+		M = eps_sm;
+		__syncthreads();
+	}
 
 	for (int k = 0; k < dim; k++) {
 		// pivot: first row r >= k with the largest |M(r, k)|  (idamax)
@@ -394,7 +403,8 @@ int ibm_compute_epsilon(life_ctx *ctx, int64_t nb, const int64_t *first, const i
 			LIFE_CUDA(ctx, cudaFuncSetAttribute(k_eps_solve_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 			k_eps_solve_cluster<<<(unsigned)(nb * EC_CLUSTER), EC_THREADS, smem, ctx->stream>>>(a);
 		} else {
-			k_eps_solve<<<(unsigned)nb, SOLVE_THREADS, 0, ctx->stream>>>(a);
+			a.smem_dim = max_dim <= 72 ? (int)max_dim : 0;      // 72^2 doubles = 41 KB: below the default dynamic shared-memory limit
+			k_eps_solve<<<(unsigned)nb, SOLVE_THREADS, sizeof(double) * (size_t)a.smem_dim * a.smem_dim, ctx->stream>>>(a);
 		}
 		ctx->launches++;
 		LIFE_CUDA(ctx, cudaGetLastError());

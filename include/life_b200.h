@@ -290,10 +290,11 @@ int life_read_restart(life_ctx *ctx, const char *path, const double *force_xy, c
 
 /* ---- structural solver of the flexible bodies -------------------------------------------------------- */
 /*
- * STATUS: new.  The solver core (csrc/fem_core.h) is checked on the CPU against the compiled reference — serially
- * for its arithmetic, as real threads under ThreadSanitizer for its barriers —, these entry points are exercised by
- * tests/test_gpu_fem.py and first short runs on a B200 agree with the reference to rounding; no default path calls them yet: the
- * host program keeps the reference's own FEM.
+ * OPTIONAL (the north star keeps the FEM host-side, and so does the host program by default).  The solver core
+ * (csrc/fem_core.h) is checked on the CPU against the compiled reference — serially for its arithmetic, as real threads under
+ * ThreadSanitizer for its barriers —, these entry points inside live runs of the compiled reference on a B200 for all four flexible
+ * examples (tests/test_gpu_fem.py), and the host program binds them with LIFE_B200_DEVICE_FEM = 1 / 2 (life_host.cpp).  Its own LU
+ * agrees with LAPACK to rounding, not bit for bit.
  *
  * One CTA per filament: FEMBodyClass::dynamicFEM (src/FEMBody.cpp:26-68: corotational 2-node beam elements, Newmark-beta,
  * Newton-Raphson over a dense LU), resetValues + predictor (:341-349, :259-289) and the Aitken-relaxed update

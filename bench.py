@@ -527,6 +527,8 @@ def run_gpu_arm(args):
     # the reference's OpenMP build on this box's host cores, beside the GPU number at EVERY N (rank 0 alone, after the other
     # ranks have finished: they exit while this runs, so the sample has the host to itself)
     torch.cuda.empty_cache()
+    if world > 1 and not args.no_cpu_baseline:
+        time.sleep(3.0)      # the other ranks are unmapping their 26 GB host images while they exit: keep that out of the CPU sample
     cpu = None if args.no_cpu_baseline else cpu_baseline_block(args.collision)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,

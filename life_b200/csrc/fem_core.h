@@ -294,10 +294,15 @@ FEM_FN void solve_system(const Body &b, Lane l) {
 		FEM_SYNC();   // every thread has read the pivot before the column below it is scaled
 		for (int i = k + 1 + l.tid; i < n; i += l.n) A[(o + i) * dim + o + k] *= inv;
 		FEM_SYNC();
-		const int m = n - k - 1;
-		for (int t = l.tid; t < m * m; t += l.n) {
-			const int i = k + 1 + t / m, j = k + 1 + t % m;
-			A[(o + i) * dim + o + j] -= A[(o + i) * dim + o + k] * A[(o + k) * dim + o + j];
+		// trailing update A[i][j] -= L[i][k] U[k][j], i, j > k: lanes walk along a row (contiguous), groups of lanes over the rows — no
+		// integer division per element (the flat index t / m, t % m used to cost more than the update itself)
+		{
+			const int W = l.n >= 32 ? 32 : 1, G = l.n / W;
+			const int lane = l.tid % W, grp = l.tid / W;
+			for (int i = k + 1 + grp; i < n; i += G) {
+				const double lik = A[(o + i) * dim + o + k];
+				for (int j = k + 1 + lane; j < n; j += W) A[(o + i) * dim + o + j] -= lik * A[(o + k) * dim + o + j];
+			}
 		}
 		// forward substitution folded in: x[i] -= L[i][k] * x[k]
 		for (int i = k + 1 + l.tid; i < n; i += l.n) x[o + i] -= A[(o + i) * dim + o + k] * x[o + k];

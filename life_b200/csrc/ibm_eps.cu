@@ -151,10 +151,10 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_eps_solve(const EpsArgs a) {
 		}
 		__syncthreads();
 		// trailing update M(r, c) -= M(r, k) * M(k, c), r, c > k; consecutive threads walk down a column (contiguous)
-		const int m = dim - k - 1;
-		for (int64_t e = tid; e < (int64_t)m * m; e += T) {
-			const int c = k + 1 + (int)(e / m), r = k + 1 + (int)(e % m);
-			M[(int64_t)c * dim + r] -= M[(int64_t)k * dim + r] * M[(int64_t)c * dim + k];
+		// (warps over the columns, lanes down a column: no integer division per element)
+		for (int c = k + 1 + (tid >> 5); c < dim; c += (T >> 5)) {
+			const double mkc = M[(int64_t)c * dim + k];
+			for (int r = k + 1 + (tid & 31); r < dim; r += 32) M[(int64_t)c * dim + r] -= M[(int64_t)k * dim + r] * mkc;
 		}
 		__syncthreads();
 	}
@@ -277,11 +277,10 @@ __global__ void __cluster_dims__(EC_CLUSTER, 1, 1) __launch_bounds__(EC_THREADS,
 			}
 		__syncthreads();
 		const int lc0 = k >= q ? (k - q) / EC_CLUSTER + 1 : 0;       // first local column with global index > k
-		const int m = dim - k - 1;
-		for (int64_t e = tid; e < (int64_t)(ncl - lc0) * m; e += T) {
-			const int lc = lc0 + (int)(e / m), r = k + 1 + (int)(e % m);
+		for (int lc = lc0 + (tid >> 5); lc < ncl; lc += (T >> 5)) {      // warps over the local columns, lanes down a column
 			double *c = col + (size_t)lc * dim;
-			c[r] -= buf[r] * c[k];
+			const double ck = c[k];
+			for (int r = k + 1 + (tid & 31); r < dim; r += 32) c[r] -= buf[r] * ck;
 		}
 		__syncthreads();
 	}

@@ -359,7 +359,7 @@ def run_gpu_arm(args):
     Dt = (1.0 / np.sqrt(3.0)) ** 2 * Dx * Dx * 0.5 / nu_p
     stream = torch.cuda.Stream(device=dev)
     cfg = capi.Config(Nx=Nx, Ny=Ny, omega=1.0, collision=coll, wall_top=capi.VELOCITY, Dx=Dx, Dt=Dt, Dm=Dx ** 3,
-                      device=local, rank=rank, nranks=world, kernel=args.kernel, inplace=1 if args.inplace else 0)
+                      device=local, rank=rank, nranks=world, kernel=args.kernel, inplace=1 if args.inplace else 0, exact=1 if args.exact else 0)
     cfg.stream = stream.cuda_stream
     ctx = capi.Context(cfg, nccl_id=nccl_id)
     nxl = ctx.nxl
@@ -534,7 +534,8 @@ def run_gpu_arm(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong" if args.global_nx > 0 else "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": dict(workload_config(S, world, args.collision), Nx=Nx, layout="in place, one population buffer (cfg.inplace)" if args.inplace else "two population buffers", **({"workload": "synthetic lid-driven cavity, global lattice %dx%d cut into %d x-slabs (strong scaling)" % (Nx, Ny, world)} if args.global_nx > 0 else {})),
+        "config": dict(workload_config(S, world, args.collision), Nx=Nx, layout="in place, one population buffer (cfg.inplace)" if args.inplace else "two population buffers",
+                       arithmetic="reference operation order, no FMA contraction (cfg.exact)" if args.exact else "factored collision, FMA", **({"workload": "synthetic lid-driven cavity, global lattice %dx%d cut into %d x-slabs (strong scaling)" % (Nx, Ny, world)} if args.global_nx > 0 else {})),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src,
                      "kernel": "k_bulk (fused stream+collide sweep)", "kernel_ms": bulk_ms, "launches_timed": bulk_n,
@@ -566,6 +567,7 @@ def main():
     ap.add_argument("--global-nx", type=int, default=0,
                     help="strong scaling: fix the global lattice at GLOBAL_NX x SIZE and cut it into --gpus slabs (default: weak scaling, SIZE x SIZE per GPU)")
     ap.add_argument("--inplace", action="store_true", help="cfg.inplace: one population buffer (72 B/node resident), in-place shift sweep")
+    ap.add_argument("--exact", action="store_true", help="cfg.exact: the step in the reference's operation order (bitwise its results)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--ref-worker", nargs=5, default=None, help=argparse.SUPPRESS)

@@ -272,8 +272,9 @@ int launch_max_speed(life_ctx *ctx, double *vmax, int32_t *has_nan, int64_t *nan
 	int64_t blocks = ((a.L.Ny + 511) / 512) * a.L.nxl;
 	const int path = ctx->stored_macro_valid ? 0 : ((a.fxy_mode == FXY_FIELD || a.fibm || a.shifted) ? 1 : 2);
 	// persistent: exactly one wave of resident blocks (a fixed 8 per SM used to run 1.6 waves at the kernel's real occupancy)
-	static int per_sm[3] = {0, 0, 0};
-	if (per_sm[path] == 0) {
+	// (queried per call: occupancy is a property of the device the context lives on, and one process may hold several)
+	int per_sm[3] = {0, 0, 0};
+	{
 		cudaError_t e = path == 0 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], k_max_speed<0>, 256, 0)
 		              : path == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], k_max_speed<1>, 256, 0)
 		                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[2], k_max_speed<2>, 256, 0);

@@ -4,7 +4,7 @@
  *
  * Arithmetic is written in the operation order of the reference so that the BGK paths reproduce the reference's
  * doubles bit for bit when both are compiled without FMA contraction (baseline x86-64; this file is built with
- * -ffp-contract=off).  The central-moments back-transform is the one deliberate exception (see cm_collide()).
+ * -ffp-contract=off) — both collision operators.
  */
 #define _USE_MATH_DEFINES
 #include "life_oracle.h"
@@ -82,14 +82,10 @@ static inline int64_t recv_id(const orc_grid *g, int64_t i, int64_t j, int v) {
  * Central-moments collision, Grid.cpp:106-233.
  * Pre-collision moments k4Pre, k5Pre: the reference's loop (Grid.cpp:113-122), same order.
  * Post-collision central moments k0..k8: Grid.cpp:125-133.
- * Back-transform: the reference writes out nine 9-term polynomials in (ux, uy) (Grid.cpp:143-223).  Those are the
- * expansion of  central moments --(binomial shift by u)--> raw moments --(D2Q9 inverse moment matrix)--> populations.
- * Here the two stages are evaluated as such (mathematically identical, ~6x fewer flops, differs from the expanded
- * form only in rounding; tests pin it to the compiled reference at 1e-13).
- *   central moments: k00=k0, k10=k1, k01=k2, k20=(k3+k4)/2, k02=(k3-k4)/2, k11=k5, k21=k6, k12=k7, k22=k8
- *   raw:  m_ab = sum_{p<=a,q<=b} C(a,p) C(b,q) ux^(a-p) uy^(b-q) k_pq
- *   f(0,0) = m00 - m20 - m02 + m22;  f(s,0) = (s m10 + m20 - s m12 - m22)/2;  f(0,s) = (s m01 + m02 - s m21 - m22)/2;
- *   f(s,r) = (s r m11 + s m12 + r m21 + m22)/4
+ * Back-transform: the reference writes out nine 9-term polynomials in (ux, uy) (Grid.cpp:143-223): the expansion of
+ *   central moments --(binomial shift by u)--> raw moments --(D2Q9 inverse moment matrix)--> populations.
+ * They are restated term by term in the reference's association (round 2; round 1 evaluated the two stages as such, 1e-15 away),
+ * so the central-moments path is bit-identical to the compiled reference as well (tests/test_oracle_vs_ref.py).
  */
 static void cm_collide(const orc_grid *g, int64_t id, double fStar[NV]) {
 	const double *fn = g->f_n + id * NV;
@@ -114,27 +110,90 @@ static void cm_collide(const orc_grid *g, int64_t id, double fStar[NV]) {
 	double k7 = 0.5 * Fx * SQ(g->c_s);
 	double k8 = rho * QU(g->c_s);
 
-	double k20 = 0.5 * (k3 + k4), k02 = 0.5 * (k3 - k4);
-	double ux2 = ux * ux, uy2 = uy * uy, uxy = ux * uy;
-	double m00 = k0;
-	double m10 = k1 + ux * k0;
-	double m01 = k2 + uy * k0;
-	double m20 = k20 + 2.0 * ux * k1 + ux2 * k0;
-	double m02 = k02 + 2.0 * uy * k2 + uy2 * k0;
-	double m11 = k5 + ux * k2 + uy * k1 + uxy * k0;
-	double m21 = k6 + 2.0 * ux * k5 + ux2 * k2 + uy * k20 + 2.0 * uxy * k1 + ux2 * uy * k0;
-	double m12 = k7 + 2.0 * uy * k5 + uy2 * k1 + ux * k02 + 2.0 * uxy * k2 + ux * uy2 * k0;
-	double m22 = k8 + 2.0 * ux * k7 + 2.0 * uy * k6 + ux2 * k02 + uy2 * k20 + 4.0 * uxy * k5 + 2.0 * ux * uy2 * k1 + 2.0 * ux2 * uy * k2 + ux2 * uy2 * k0;
-
-	fStar[0] = m00 - m20 - m02 + m22;
-	fStar[1] = 0.5 * (m10 + m20 - m12 - m22);
-	fStar[2] = 0.5 * (-m10 + m20 + m12 - m22);
-	fStar[3] = 0.5 * (m01 + m02 - m21 - m22);
-	fStar[4] = 0.5 * (-m01 + m02 + m21 - m22);
-	fStar[5] = 0.25 * (m11 + m12 + m21 + m22);
-	fStar[6] = 0.25 * (m11 - m12 - m21 + m22);
-	fStar[7] = 0.25 * (-m11 + m12 - m21 + m22);
-	fStar[8] = 0.25 * (-m11 - m12 + m21 + m22);
+	/* back-transform: the reference's nine expanded polynomials (Grid.cpp:143-223), every sum and product associated as the
+	 * reference's expressions parse; x = ux, y = uy, xx = SQ(ux), yy = SQ(uy) */
+	const double x = ux, y = uy, xx = ux * ux, yy = uy * uy;
+	fStar[0] = (xx * yy - xx - yy + 1.0) * k0
+	     + (2.0 * x * yy - 2.0 * x) * k1
+	     + (2.0 * y * xx - 2.0 * y) * k2
+	     + (0.5 * xx + 0.5 * yy - 1.0) * k3
+	     + (0.5 * yy - 0.5 * xx) * k4
+	     + 4.0 * x * y * k5
+	     + 2.0 * y * k6
+	     + 2.0 * x * k7
+	     + k8;
+	fStar[1] = (0.5 * xx - 0.5 * (xx * yy) - 0.5 * (x * yy) + 0.5 * x) * k0
+	     + (x - x * yy - 0.5 * yy + 0.5) * k1
+	     + (-y * xx - y * x) * k2
+	     + (-0.25 * xx - 0.25 * x - 0.25 * yy + 0.25) * k3
+	     + (0.25 * xx + 0.25 * x - 0.25 * yy + 0.25) * k4
+	     + (-y - 2.0 * x * y) * k5
+	     + (-y) * k6
+	     + (-x - 0.5) * k7
+	     - 0.5 * k8;
+	fStar[2] = (-0.5 * (xx * yy) + 0.5 * xx + 0.5 * (x * yy) - 0.5 * x) * k0
+	     + (x - x * yy + 0.5 * yy - 0.5) * k1
+	     + (-y * xx + y * x) * k2
+	     + (-0.25 * xx + 0.25 * x - 0.25 * yy + 0.25) * k3
+	     + (0.25 * xx - 0.25 * x - 0.25 * yy + 0.25) * k4
+	     + (y - 2.0 * x * y) * k5
+	     + (-y) * k6
+	     + (0.5 - x) * k7
+	     - 0.5 * k8;
+	fStar[3] = (0.5 * yy - 0.5 * (xx * y) - 0.5 * (xx * yy) + 0.5 * y) * k0
+	     + (-x * yy - x * y) * k1
+	     + (y - xx * y - 0.5 * xx + 0.5) * k2
+	     + (-0.25 * xx - 0.25 * yy - 0.25 * y + 0.25) * k3
+	     + (0.25 * xx - 0.25 * yy - 0.25 * y - 0.25) * k4
+	     + (-x - 2.0 * x * y) * k5
+	     + (-y - 0.5) * k6
+	     + (-x) * k7
+	     - 0.5 * k8;
+	fStar[4] = (-0.5 * (xx * yy) + 0.5 * (xx * y) + 0.5 * yy - 0.5 * y) * k0
+	     + (-x * yy + x * y) * k1
+	     + (y - xx * y + 0.5 * xx - 0.5) * k2
+	     + (-0.25 * xx - 0.25 * yy + 0.25 * y + 0.25) * k3
+	     + (0.25 * xx - 0.25 * yy + 0.25 * y - 0.25) * k4
+	     + (x - 2.0 * x * y) * k5
+	     + (0.5 - y) * k6
+	     + (-x) * k7
+	     - 0.5 * k8;
+	fStar[5] = (0.25 * (xx * yy) + 0.25 * (xx * y) + 0.25 * (x * yy) + 0.25 * (x * y)) * k0
+	     + (0.25 * y + 0.5 * (x * y) + 0.5 * (x * yy) + 0.25 * yy) * k1
+	     + (0.25 * x + 0.5 * (x * y) + 0.5 * (xx * y) + 0.25 * xx) * k2
+	     + (0.125 * xx + 0.125 * x + 0.125 * yy + 0.125 * y) * k3
+	     + (-0.125 * xx - 0.125 * x + 0.125 * yy + 0.125 * y) * k4
+	     + (0.5 * x + 0.5 * y + x * y + 0.25) * k5
+	     + (0.5 * y + 0.25) * k6
+	     + (0.5 * x + 0.25) * k7
+	     + 0.25 * k8;
+	fStar[6] = (0.25 * (xx * yy) - 0.25 * (xx * y) - 0.25 * (x * yy) + 0.25 * (x * y)) * k0
+	     + (0.25 * y - 0.5 * (x * y) + 0.5 * (x * yy) - 0.25 * yy) * k1
+	     + (0.25 * x - 0.5 * (x * y) + 0.5 * (xx * y) - 0.25 * xx) * k2
+	     + (0.125 * xx - 0.125 * x + 0.125 * yy - 0.125 * y) * k3
+	     + (-0.125 * xx + 0.125 * x + 0.125 * yy - 0.125 * y) * k4
+	     + (x * y - 0.5 * y - 0.5 * x + 0.25) * k5
+	     + (0.5 * y - 0.25) * k6
+	     + (0.5 * x - 0.25) * k7
+	     + 0.25 * k8;
+	fStar[7] = (0.25 * (xx * yy) - 0.25 * (xx * y) + 0.25 * (x * yy) - 0.25 * (x * y)) * k0
+	     + (0.5 * (x * yy) - 0.5 * (x * y) - 0.25 * y + 0.25 * yy) * k1
+	     + (0.5 * (x * y) - 0.25 * x + 0.5 * (xx * y) - 0.25 * xx) * k2
+	     + (0.125 * xx + 0.125 * x + 0.125 * yy - 0.125 * y) * k3
+	     + (-0.125 * xx - 0.125 * x + 0.125 * yy - 0.125 * y) * k4
+	     + (0.5 * y - 0.5 * x + x * y - 0.25) * k5
+	     + (0.5 * y - 0.25) * k6
+	     + (0.5 * x + 0.25) * k7
+	     + 0.25 * k8;
+	fStar[8] = (0.25 * (xx * yy) + 0.25 * (xx * y) - 0.25 * (x * yy) - 0.25 * (x * y)) * k0
+	     + (0.5 * (x * y) - 0.25 * y + 0.5 * (x * yy) - 0.25 * yy) * k1
+	     + (0.5 * (xx * y) - 0.5 * (x * y) - 0.25 * x + 0.25 * xx) * k2
+	     + (0.125 * xx - 0.125 * x + 0.125 * yy + 0.125 * y) * k3
+	     + (-0.125 * xx + 0.125 * x + 0.125 * yy + 0.125 * y) * k4
+	     + (0.5 * x - 0.5 * y + x * y - 0.25) * k5
+	     + (0.5 * y + 0.25) * k6
+	     + (0.5 * x - 0.25) * k7
+	     + 0.25 * k8;
 }
 
 /* stream + collide of one node (push), Grid.cpp:103-246 */

@@ -53,8 +53,7 @@ def test_inplace_exact_mode_is_bitwise_the_reference(case):
     o.step(N)
     st = a.download_state()
     for name in ("rho", "u", "f"):
-        if not int(g["central_moments"]):      # (the oracle's central-moments path is factored: only the fixtures are the reference's bits)
-            assert np.array_equal(st[name], o.get(name)), (case, name, K.rel_l2(st[name], o.get(name)))
+        assert np.array_equal(st[name], o.get(name)), (case, name, K.rel_l2(st[name], o.get(name)))
         assert np.array_equal(K.sampled(st[name], g), g[name]), (case, "golden " + name)
     a.close()
 

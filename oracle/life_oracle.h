@@ -15,8 +15,8 @@
  * linear indices are 64-bit (the reference's int overflows above 15446^2).
  *
  * Parity pin: tests/test_oracle_vs_ref.py checks this file against the compiled, unmodified reference
- * (oracle/_ref/libref_<case>.so) for all seven shipped examples and nine extra cases — BGK paths bit for bit,
- * central-moments paths to 1e-13 (the back-transform is evaluated in factored form here) — and against the
+ * (oracle/_ref/libref_<case>.so) for all seven shipped examples and the extra cases — bit for bit for both collision
+ * operators (round 2: the central-moments back-transform follows the reference's association too) — and against the
  * fixtures under tests/golden/ that the same reference build generated (tests/golden/make_golden.py).
  */
 #ifndef LIFE_ORACLE_H

@@ -290,30 +290,33 @@ FEM_FN void solve_system(const Body &b, Lane l) {
 			if (l.tid == 0) { const double t = x[o + k]; x[o + k] = x[o + p]; x[o + p] = t; }
 			FEM_SYNC();
 		}
-		const double inv = 1.0 / A[(o + k) * dim + o + k];
-		FEM_SYNC();   // every thread has read the pivot before the column below it is scaled
-		for (int i = k + 1 + l.tid; i < n; i += l.n) A[(o + i) * dim + o + k] *= inv;
-		FEM_SYNC();
-		// trailing update A[i][j] -= L[i][k] U[k][j], i, j > k: lanes walk along a row (contiguous), groups of lanes over the rows — no
-		// integer division per element (the flat index t / m, t % m used to cost more than the update itself)
+		// One phase for everything below the pivot row: a row belongs to one group of lanes, which forms the multiplier L[i][k] from
+		// the UNSCALED entry (every lane on its own; it is not written back — L is never read again, the forward substitution is
+		// folded in here), updates the row and the right-hand side.  Lanes walk along the row (contiguous), no integer division per
+		// element.  Three barriers per column instead of five.
 		{
+			const double inv = 1.0 / A[(o + k) * dim + o + k];
 			const int W = l.n >= 32 ? 32 : 1, G = l.n / W;
 			const int lane = l.tid % W, grp = l.tid / W;
 			for (int i = k + 1 + grp; i < n; i += G) {
-				const double lik = A[(o + i) * dim + o + k];
+				const double lik = A[(o + i) * dim + o + k] * inv;
 				for (int j = k + 1 + lane; j < n; j += W) A[(o + i) * dim + o + j] -= lik * A[(o + k) * dim + o + j];
+				if (lane == 0) x[o + i] -= lik * x[o + k];
 			}
 		}
-		// forward substitution folded in: x[i] -= L[i][k] * x[k]
-		for (int i = k + 1 + l.tid; i < n; i += l.n) x[o + i] -= A[(o + i) * dim + o + k] * x[o + k];
 		FEM_SYNC();
 	}
-	for (int k = n - 1; k >= 0; k--) {   // back substitution
-		if (l.tid == 0) x[o + k] /= A[(o + k) * dim + o + k];
-		FEM_SYNC();
-		for (int i = l.tid; i < k; i += l.n) x[o + i] -= A[(o + i) * dim + o + k] * x[o + k];
+	// back substitution, one barrier per column: x[k] / U[k][k] is formed by every thread (nobody writes x[k] any more), kept in
+	// `work`, and the rows above are updated
+	double *y = b.work;
+	for (int k = n - 1; k >= 0; k--) {
+		const double xk = x[o + k] / A[(o + k) * dim + o + k];
+		if (l.tid == 0) y[k] = xk;
+		for (int i = l.tid; i < k; i += l.n) x[o + i] -= A[(o + i) * dim + o + k] * xk;
 		FEM_SYNC();
 	}
+	for (int i = l.tid; i < n; i += l.n) x[o + i] = y[i];
+	FEM_SYNC();
 }
 
 // FEMBodyClass::finishNewmark, src/FEMBody.cpp:129-144

@@ -214,3 +214,85 @@ def test_file_plan_tiles_the_file_exactly(lib_built):
             assert spans[0][0] == 0 and spans[-1][1] == total
             for a, b in zip(spans, spans[1:]):
                 assert a[1] == b[0], (kind, Nx, Ny, world, a, b)      # no gap, no overlap
+
+
+# ---- the in-place ("shift") layout of cfg.inplace, as a numpy model executed by real ranks -------------------------------------------
+def _inplace_worker(rank, world, port, Nx, Ny, steps, out_dir):
+    """One population buffer per rank: population v of logical element n sits at plane element (n - off_v) mod S (csrc/ctx.h:
+    PopShift).  A step = every node keeps its nine values where they are (omega = 0: collision is the identity), the offsets grow by
+    shift_v = cx*P + cy (that IS the push), then y-wrap, x-halo through contiguous staging (the planes are circular, halo.cu:
+    k_halo_pack / k_halo_unpack) — all in the logical view.  After `steps` steps over gloo the lattice must equal `steps` applications
+    of the reference's push map (src/Grid.cpp:229,240)."""
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from life_b200 import capi, dist as D
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        b, e = capi.slab_range(Nx, world, rank)
+        nxl = e - b
+        JOFF = 2
+        P = Ny + 4                      # column pitch with ghost rows at JOFF-1 and JOFF+Ny (the library pads to a multiple of 16)
+        S = (nxl + 2) * P               # plane size, ghost columns 0 and nxl+1
+        planes = np.zeros((9, S))
+        off = np.zeros(9, dtype=np.int64)
+        at = lambda v, idx: (idx - off[v]) % S                       # PopShift::at
+        node = lambda c, r: c * P + r
+        tags = np.arange(1, Nx * Ny * 9 + 1, dtype=np.float64).reshape(Nx, Ny, 9)
+        cols = np.arange(1, nxl + 1)[:, None]
+        rows = (JOFF + np.arange(Ny))[None, :]
+        own = node(cols, rows)                                        # logical element of every owned node
+        for v in range(9):
+            planes[v, at(v, own)] = tags[b:e, :, v]                  # upload: plain layout (offsets zero)
+        plan = D.halo_plan(Nx, Ny, world, periodic_x=True)
+        allc = np.arange(nxl + 2)
+        for _ in range(steps):
+            # the sweep: in place, nothing moves; streaming = the offsets advance
+            for v in range(9):
+                off[v] = (off[v] + CX[v] * P + CY[v]) % S
+            # y wrap of every column incl. the ghost columns (k_wrap_y), logical view
+            for v in range(9):
+                if CY[v] == 1:
+                    planes[v, at(v, node(allc, JOFF))] = planes[v, at(v, node(allc, JOFF + Ny))]
+                elif CY[v] == -1:
+                    planes[v, at(v, node(allc, JOFF + Ny - 1))] = planes[v, at(v, node(allc, JOFF - 1))]
+            # x halo: gather the ghost columns into contiguous buffers, ship, scatter into the edge columns
+            r = JOFF + np.arange(Ny)
+            reqs, bufs = [], []
+            for (src, dst, pops, n) in plan:
+                if src == rank:
+                    col = nxl + 1 if pops == (1, 5, 7) else 0
+                    msg = torch.from_numpy(np.stack([planes[v, at(v, node(col, r))] for v in pops]).copy())
+                    reqs.append(dist.isend(msg, dst=dst, tag=0 if pops == (1, 5, 7) else 1))
+                if dst == rank:
+                    buf = torch.empty((3, Ny), dtype=torch.float64)
+                    reqs.append(dist.irecv(buf, src=src, tag=0 if pops == (1, 5, 7) else 1))
+                    bufs.append((pops, buf))
+            for q in reqs:
+                q.wait()
+            for pops, buf in bufs:
+                col = 1 if pops == (1, 5, 7) else nxl
+                for k, v in enumerate(pops):
+                    planes[v, at(v, node(col, r))] = buf[k].numpy()
+        got = np.stack([planes[v, at(v, own)] for v in range(9)], axis=-1)       # download through the shifted layout (k_pack)
+        full = D.gather_slabs(np.ascontiguousarray(got), Nx)
+        if rank == 0:
+            expect = tags
+            i, j = np.meshgrid(np.arange(Nx), np.arange(Ny), indexing="ij")
+            for _ in range(steps):
+                nxt = np.zeros_like(expect)
+                for v in range(9):
+                    nxt[(i + CX[v] + Nx) % Nx, (j + CY[v] + Ny) % Ny, v] = expect[i, j, v]
+                expect = nxt
+            assert np.array_equal(full, expect)
+            open(os.path.join(out_dir, "ok_inplace"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,shape,steps", [(2, (12, 7), 5), (3, (13, 5), 4), (2, (9, 16), 7)])
+def test_inplace_layout_design_over_gloo(world, shape, steps, tmp_path, lib_built):
+    import torch.multiprocessing as mp
+    Nx, Ny = shape
+    mp.spawn(_inplace_worker, args=(world, _free_port(), Nx, Ny, steps, str(tmp_path)), nprocs=world, join=True)
+    assert (tmp_path / "ok_inplace").exists()
